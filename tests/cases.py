@@ -1,0 +1,34 @@
+"""Seeded synthetic NMS inputs shared by the golden generator and the tests
+(distribution from SURVEY.md section 8d: one dominant class per anchor, others <= 9e-4)."""
+import torch
+
+
+def synth_pred(B, A, nc, S, seed, quant=None, neg=False, wide=False):
+    g = torch.Generator().manual_seed(seed)
+    p = torch.zeros(B, A, 4 + nc)
+    p[..., 0:2] = torch.rand(B, A, 2, generator=g) * S
+    p[..., 2:4] = torch.rand(B, A, 2, generator=g) * ((0.6 if wide else 0.2) * S) + 4
+    if neg:                       # boxes hanging over the top/left edge -> negative x1/y1
+        p[..., 0:2] -= 0.15 * S
+    p[..., 4:] = torch.rand(B, A, nc, generator=g) * 9e-4
+    dom = torch.randint(0, nc, (B, A), generator=g)
+    sc = torch.rand(B, A, generator=g)
+    if quant:                     # heavy score ties
+        sc = torch.round(sc * quant) / quant
+    p.scatter_(2, (dom + 4).unsqueeze(-1), sc.unsqueeze(-1))
+    return p
+
+
+NMS_CASES = {
+    "plain":      dict(gen=dict(B=2, A=2000, nc=80, S=640, seed=3), kw=dict(conf_thres=0.25, iou_thres=0.45)),
+    "ties":       dict(gen=dict(B=2, A=3000, nc=80, S=640, seed=4, quant=64), kw=dict(conf_thres=0.25, iou_thres=0.45)),
+    "few_cls_neg": dict(gen=dict(B=2, A=3000, nc=3, S=640, seed=5, quant=16, neg=True), kw=dict(conf_thres=0.05, iou_thres=0.45)),
+    "stress":     dict(gen=dict(B=1, A=8400, nc=80, S=640, seed=6, neg=True), kw=dict(conf_thres=0.001, iou_thres=0.6)),
+    "agnostic":   dict(gen=dict(B=2, A=1500, nc=80, S=640, seed=7, quant=32), kw=dict(conf_thres=0.25, iou_thres=0.45, agnostic=True)),
+    "classes":    dict(gen=dict(B=2, A=1500, nc=80, S=640, seed=8), kw=dict(conf_thres=0.25, iou_thres=0.45, classes=[1, 5, 7])),
+    "empty":      dict(gen=dict(B=2, A=500, nc=80, S=640, seed=9), kw=dict(conf_thres=0.99999, iou_thres=0.45)),
+    "iou0":       dict(gen=dict(B=1, A=1000, nc=4, S=64, seed=10, quant=8, neg=True), kw=dict(conf_thres=0.1, iou_thres=0.0)),
+    "iou1":       dict(gen=dict(B=1, A=1000, nc=4, S=64, seed=11, quant=8, neg=True), kw=dict(conf_thres=0.1, iou_thres=1.0)),
+    "small_maxdet": dict(gen=dict(B=2, A=1200, nc=20, S=320, seed=12, wide=True), kw=dict(conf_thres=0.2, iou_thres=0.5, max_det=17)),
+    "few_keep":   dict(gen=dict(B=3, A=900, nc=2, S=96, seed=13, wide=True), kw=dict(conf_thres=0.3, iou_thres=0.3)),
+}

@@ -1,0 +1,123 @@
+"""CPU tests that pin the ORACLE: against fixtures produced by the real reference
+(tests/golden/), against the reference's own live known-answer tests (tests/test_heads.py in
+the reference checkout), against torchvision, and -- where /root/reference is mounted --
+against the reference itself, bit for bit."""
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gelan_ref as G
+from oracle import nms_ref as N
+from tests.cases import NMS_CASES, synth_pred
+from tests.conftest import HAVE_REFERENCE, ROOT
+
+GOLD = Path(__file__).parent / "golden"
+
+
+# ---- known answers the reference's own tests hold (reference tests/test_heads.py) -----------
+def test_anchor_known_answers():
+    pts, st = G.anchors_and_strides([(80, 80), (40, 40), (20, 20)], [8, 16, 32], torch.float32)
+    assert pts.shape == (8400, 2) and st.shape == (8400, 1)            # test_heads.py:42-44
+    assert pts[0].tolist() == [0.5, 0.5]                               # test_heads.py:46-49
+    assert st[:6400].eq(8).all() and st[6400:8000].eq(16).all() and st[8000:].eq(32).all()  # :51-55
+
+
+def test_dfl_range_and_known_box():
+    w = torch.arange(16.).view(1, 16, 1, 1)
+    e = G.dfl_expectation(torch.randn(2, 64, 100, generator=torch.Generator().manual_seed(0)) * 3, w)
+    assert e.shape == (2, 4, 100) and e.min() >= 0 and e.max() <= 15   # test_heads.py:19-27
+    # ltrb = 1 at anchor (5,5): xyxy (4,4,6,6) (test_heads.py:71-79) == xywh (5,5,2,2); stride 1.
+    # A one-hot-at-bin-1 distribution makes the DFL expectation exactly 1.
+    raw = torch.full((1, 64 + 2, 11, 11), -1e4)
+    raw[:, 1:64:16] = 1e4
+    y = G.decode([raw], [1.0], 2, w)
+    a = 5 * 11 + 5 - 0  # anchor at x=5.5,y=5.5 -> use exact arithmetic instead:
+    assert torch.allclose(y[0, :4, a], torch.tensor([5.5, 5.5, 2.0, 2.0]))
+
+
+# ---- network forward vs reference-generated fixtures ------------------------------------------
+@pytest.mark.parametrize("name,fix", [("gelan-c_128", "gelan_c"), ("gelan-c_640", "gelan_c"), ("yolov9-c_64", "yolov9_c")])
+def test_forward_matches_reference_fixture(name, fix, request):
+    nodes, nc, sd = request.getfixturevalue(fix)
+    gd = np.load(GOLD / f"{name}.npz", allow_pickle=False)
+    x = G.fractal(int(gd["batch"]), int(gd["size"]), torch.Generator().manual_seed(int(gd["seed"])))
+    cap = {}
+    y, raws = G.forward(nodes, nc, sd, x, capture=cap)
+    if isinstance(y, list):
+        y, raws = y[1], raws[1]
+    sa = int(gd["stride_a"])
+    # Same torch build => bit-equal here; a different host CPU may pick other conv kernels, so
+    # the gate is the reference's own fp32-vs-fp64 floor recorded in the fixture (x4 slack).
+    tol_box = max(4 * float(gd["floor_box"]), 1e-3)
+    tol_sc = max(4 * float(gd["floor_score"]), 1e-5)
+    ysub = y[:, :, ::sa].numpy()
+    assert np.abs(ysub[:, :4] - gd["y_sub"][:, :4]).max() <= tol_box
+    assert np.abs(ysub[:, 4:] - gd["y_sub"][:, 4:]).max() <= tol_sc
+    for n, am in zip(gd["layer_names"], gd["layer_absmean"]):
+        assert abs(cap[str(n)].abs().mean().item() - am) <= 1e-4 * max(am, 1e-3), n
+    for i, r in enumerate(raws):
+        s = max(1, sa // 2)
+        assert np.abs(r[:, :, ::s, ::s].numpy() - gd[f"raw{i}_sub"]).max() <= 1e-3
+    if sa == 1:   # detections of the reference's NMS on the reference's y
+        dets = N.non_max_suppression(torch.from_numpy(gd["y_sub"]).permute(0, 2, 1).contiguous(), 0.25, 0.45)
+        for i, d in enumerate(dets):
+            assert np.array_equal(d, gd[f"det{i}"])
+
+
+# ---- NMS ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(NMS_CASES))
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_nms_matches_reference_fixture(name, impl):
+    gd = np.load(GOLD / "nms_cases.npz")
+    c = NMS_CASES[name]
+    p = synth_pred(**c["gen"])
+    dets, keeps = N.non_max_suppression(p, impl=impl, return_keep=True, **c["kw"])
+    for i, (d, k) in enumerate(zip(dets, keeps)):
+        assert np.array_equal(d, gd[f"{name}.{i}"]), (name, i)
+        assert np.array_equal(p[i, k, 4:].max(1).values.numpy(), d[:, 4])   # keep indices point at the rows
+
+
+def test_greedy_nms_equals_torchvision():
+    tv = pytest.importorskip("torchvision")
+    g = torch.Generator().manual_seed(0)
+    for quant in (None, 16):
+        b = torch.rand(1500, 4, generator=g) * 300
+        b[:, 2:] = b[:, :2] + torch.rand(1500, 2, generator=g) * 120
+        s = torch.rand(1500, generator=g)
+        if quant:
+            s = torch.round(s * quant) / quant
+        for thr in (0.0, 0.3, 0.45, 0.7):
+            assert np.array_equal(tv.ops.nms(b, s, thr).numpy(), N.greedy_nms_numpy(b.numpy(), s.numpy(), thr))
+
+
+# ---- the reference itself (build container only) -------------------------------------------------
+@pytest.mark.reference
+@pytest.mark.skipif(not HAVE_REFERENCE, reason="/root/reference not mounted")
+@pytest.mark.parametrize("cfg,fix", [("gelan-c", "gelan_c"), ("yolov9-c", "yolov9_c")])
+def test_bit_equal_to_reference(cfg, fix, request):
+    sys.modules.setdefault("albumentations", types.ModuleType("albumentations"))
+    sys.path.insert(0, "/root/reference/src")
+    from yolo import YOLO, non_max_suppression
+    nodes, nc, sd = request.getfixturevalue(fix)
+    m = YOLO.from_yaml(f"/root/reference/configs/models/{cfg}.yaml")
+    assert list(m.state_dict().keys()) == list(G.param_schema(nodes, nc).keys())
+    assert m.layers["detect"].stride.tolist() == G.detect_strides(nodes)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = G.fractal(1, 160, torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        yr, rr = m(x)
+    yo, ro = G.forward(nodes, nc, sd, x)
+    if cfg == "yolov9-c":
+        assert all(torch.equal(a, b) for a, b in zip(yr, yo))
+        yr, yo = yr[1], yo[1]
+    else:
+        assert all(torch.equal(a, b) for a, b in zip(rr, ro))
+    assert torch.equal(yr, yo)
+    pred = yr.permute(0, 2, 1).contiguous()
+    for a, b in zip(non_max_suppression(pred, 0.25, 0.45), N.non_max_suppression(pred, 0.25, 0.45)):
+        assert np.array_equal(a.numpy(), b)
