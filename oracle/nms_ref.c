@@ -26,7 +26,7 @@ static inline float fmin2(float a, float b) { return a < b ? a : b; }
 
 /* pred [A][4+nc] fp32. classes may be NULL (n_classes < 0 => no filter).
  * det [max_det][6], keep_anchor [max_det]. Returns number of detections, <0 on error. */
-int yre_oracle_nms_image(const float* pred, int A, int nc, float conf_thres, float iou_thres, int max_det,
+int yre_oracle_nms_image(const float* pred, int A, int nc, float conf_thres, double iou_thres, int max_det,
                          const int32_t* classes, int n_classes, int agnostic,
                          float* det, int64_t* keep_anchor)
 {
@@ -86,7 +86,7 @@ int yre_oracle_nms_image(const float* pred, int A, int nc, float conf_thres, flo
             const float h = fmax2(0.f, fmin2(oi[3], oj[3]) - fmax2(oi[1], oj[1]));
             const float inter = w * h;
             const float iou = inter / (ai + area[j] - inter);
-            if (iou > iou_thres) dead[j] = 1;
+            if ((double)iou > iou_thres) dead[j] = 1;   /* fp32 IoU vs DOUBLE threshold, as torchvision's CPU kernel */
         }
     }
     free(c); free(cls); free(box); free(nb); free(area); free(dead);

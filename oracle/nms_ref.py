@@ -6,7 +6,8 @@ The greedy step itself is third-party in the reference: ``torchvision.ops.nms``
 src/yolo/utils/nms.py:99-102, with the in-tree ``_nms_pure``/``_box_iou``
 (nms.py:107-152) as its semantic restatement.  torchvision's published algorithm, restated
 here: stable descending sort of the scores; walk the sorted list; a box is kept iff no
-previously *kept* box has ``inter / (area_i + area_j - inter) > iou_thres`` with
+previously *kept* box has ``double(inter / (area_i + area_j - inter)) > iou_thres`` (fp32 IoU
+compared against the threshold as a double -- verified against torchvision's CPU kernel) with
 ``inter = max(0, min(x2)-max(x1)) * max(0, min(y2)-max(y1))`` -- all in fp32.
 
 Two implementations with identical results:
@@ -38,7 +39,7 @@ def greedy_nms_numpy(boxes: np.ndarray, scores: np.ndarray, iou_thres: float) ->
     order = np.argsort(-scores.astype(np.float32), kind="stable")
     x1, y1, x2, y2 = (boxes[:, i] for i in range(4))
     area = (x2 - x1) * (y2 - y1)
-    thr = np.float32(iou_thres)
+    thr = float(iou_thres)            # torchvision's CPU kernel compares the fp32 IoU against the DOUBLE threshold
     dead = np.zeros(len(boxes), bool)
     keep = []
     for pos, i in enumerate(order):
@@ -51,7 +52,7 @@ def greedy_nms_numpy(boxes: np.ndarray, scores: np.ndarray, iou_thres: float) ->
         inter = w * h
         with np.errstate(divide="ignore", invalid="ignore"):
             iou = inter / (area[i] + area[rest] - inter)
-        dead[rest[iou > thr]] = True
+        dead[rest[iou.astype(np.float64) > thr]] = True
     return np.asarray(keep, np.int64)
 
 
@@ -93,7 +94,7 @@ def _lib():
         _LIB = ctypes.CDLL(str(so))
         _LIB.yre_oracle_nms_image.restype = ctypes.c_int
         _LIB.yre_oracle_nms_image.argtypes = [
-            ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+            ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_int,
             ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     return _LIB
 

@@ -31,4 +31,28 @@ NMS_CASES = {
     "iou1":       dict(gen=dict(B=1, A=1000, nc=4, S=64, seed=11, quant=8, neg=True), kw=dict(conf_thres=0.1, iou_thres=1.0)),
     "small_maxdet": dict(gen=dict(B=2, A=1200, nc=20, S=320, seed=12, wide=True), kw=dict(conf_thres=0.2, iou_thres=0.5, max_det=17)),
     "few_keep":   dict(gen=dict(B=3, A=900, nc=2, S=96, seed=13, wide=True), kw=dict(conf_thres=0.3, iou_thres=0.3)),
+    "at_thr_0.6": dict(gen="at_threshold", kw=dict(conf_thres=0.25, iou_thres=0.6)),
+    "at_thr_0.45": dict(gen="at_threshold", kw=dict(conf_thres=0.25, iou_thres=0.45)),
+    "at_thr_agn": dict(gen="at_threshold", kw=dict(conf_thres=0.25, iou_thres=0.6, agnostic=True)),
 }
+
+
+def make_pred(case):
+    return at_threshold_pred() if case["gen"] == "at_threshold" else synth_pred(**case["gen"])
+
+
+def at_threshold_pred(nc=4):
+    """Pairs whose fp32 IoU equals float32(thr) exactly, with float32(thr) > thr (thr=0.6) or
+    < thr (thr=0.45): the reference (torchvision CPU) compares the fp32 IoU with the threshold as a
+    DOUBLE, so the 0.6 pair is suppressed although `iou > float32(0.6)` is false."""
+    import numpy as np
+    rows = []
+    for k, thr in enumerate((0.6, 0.45, 0.6, 0.45)):
+        t = float(np.float32(thr))
+        x0 = 100.0 * k
+        # box A: unit square scaled by 32; box B: same height, width t -> inter = t*A, union = A
+        for w, sc in ((32.0, 0.9 - 0.01 * k), (32.0 * t, 0.8 - 0.01 * k)):
+            row = [x0 + w / 2, 16.0, w, 32.0] + [0.0] * nc
+            row[4 + (k % nc)] = sc
+            rows.append(row)
+    return torch.tensor([rows], dtype=torch.float32)

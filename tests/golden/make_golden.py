@@ -21,7 +21,7 @@ sys.path.insert(0, str(ROOT))
 
 from yolo import YOLO, non_max_suppression  # noqa: E402  (the reference)
 from oracle import gelan_ref as G           # noqa: E402
-from tests.cases import NMS_CASES, synth_pred  # noqa: E402
+from tests.cases import NMS_CASES, make_pred  # noqa: E402
 
 OUT = Path(__file__).resolve().parent
 torch.set_num_threads(8)
@@ -70,7 +70,7 @@ def net_case(cfg: str, size: int, batch: int, seed: int, stride_a: int):
 def nms_cases():
     d = {}
     for name, c in NMS_CASES.items():
-        p = synth_pred(**c["gen"])
+        p = make_pred(c)
         dets = non_max_suppression(p, **c["kw"])
         for i, t in enumerate(dets):
             d[f"{name}.{i}"] = t.numpy()

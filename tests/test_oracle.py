@@ -12,7 +12,7 @@ import torch
 
 from oracle import gelan_ref as G
 from oracle import nms_ref as N
-from tests.cases import NMS_CASES, synth_pred
+from tests.cases import NMS_CASES, make_pred
 from tests.conftest import HAVE_REFERENCE, ROOT
 
 GOLD = Path(__file__).parent / "golden"
@@ -74,7 +74,7 @@ def test_forward_matches_reference_fixture(name, fix, request):
 def test_nms_matches_reference_fixture(name, impl):
     gd = np.load(GOLD / "nms_cases.npz")
     c = NMS_CASES[name]
-    p = synth_pred(**c["gen"])
+    p = make_pred(c)
     dets, keeps = N.non_max_suppression(p, impl=impl, return_keep=True, **c["kw"])
     for i, (d, k) in enumerate(zip(dets, keeps)):
         assert np.array_equal(d, gd[f"{name}.{i}"]), (name, i)

@@ -1,0 +1,522 @@
+// K1 (product engine): implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 / TMEM),
+// operands staged by TMA, fused epilogue.
+//
+//   y = [res +] act(conv(x, w) + bias)      reference: src/yolo/blocks/conv.py:88-89 (+ conv.py:140-141,
+//                                           bottleneck.py:49-51, heads/detect.py:52,61, auxiliary.py:61-62)
+//
+// GEMM view      D[M x N] = A[M x K] * W[N x K]^T,  M = output pixels, N = Cout, K = taps * Cin.
+// A tile         128 output pixels = a (tb images) x (th rows) x (tw cols) patch; for filter tap
+//                (dy,dx) and channel chunk kc ONE TMA box {BLOCK_K ch, tw, th, tb} shifted by the tap
+//                offset is loaded straight from the NHWC activation -- out-of-bounds coordinates are
+//                zero-filled by the TMA unit, which *is* the conv padding (no im2col buffer, no halo).
+//                Stride-2 convs read a parity-plane (YRE_PHASE4) input, so each tap is again a
+//                unit-stride box (5-D tensor map, plane index = tap parity).
+// W tile         {BLOCK_K, BLOCK_N} box of the K-major [Cout][taps*Cin] weight matrix.
+// Both land in 128B- (BLOCK_K=64) or 64B- (BLOCK_K=32) swizzled shared memory that the UMMA smem
+// descriptors read directly.  Accumulators live in TMEM (2 x 256 columns, double-buffered), so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over a static tile schedule):
+//   warp 0 lane 0 : TMA producer          warp 1 lane 0 : tcgen05.mma issuer
+//   warp 2        : TMEM alloc / dealloc  warps 4..7     : epilogue (TMEM lane quarter = warp % 4)
+// Epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16/fp32 -> global, written into the
+// consumer's channel window (concat-slice write).
+#include "yre_common.cuh"
+#include <cuda.h>
+#include <cstring>
+#include <cstdlib>
+
+struct ConvTcPlan;
+
+namespace {
+
+constexpr int NUM_THREADS = 256;
+constexpr int BLOCK_M = 128;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;     // columns between the two accumulator buffers
+
+struct TcParams {
+    int tw, th, tb;                 // tile patch; tw*th*tb == 128
+    int tiles_x, tiles_y, tiles_b, tiles_n, num_tiles;
+    int Ho, Wo, B;
+    int taps, kchunks, block_k, block_n, stages;
+    int phase4;                     // stride-2 conv reading parity planes
+    int x_coff, Cin;
+    uint32_t a_bytes, b_bytes;
+    uint32_t sbo16;                 // stride-byte-offset >> 4 of the smem descriptors
+    uint32_t layout_type;           // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+    uint32_t idesc;                 // tcgen05 instruction descriptor
+    const float* bias;
+    int act;
+    void* y; int y_f32; int y_ctot, y_coff;
+    const void* res; int res_f32; int res_ctot, res_coff;
+    int* dbg;                       // optional watchdog record (may be null)
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Waits on an mbarrier phase.  A pipeline bug must never hang the GPU: after ~2 s the wait records
+// where it was stuck and traps (the launch then fails with an error instead of spinning forever).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int code) {
+    if (mbar_try(bar, parity)) return;
+    unsigned long long t0 = 0;
+    int spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if (++spins == 4096) {
+            spins = 0;
+            const unsigned long long now = gtimer();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) {
+                if (dbg) { dbg[0] = code; dbg[1] = (int)blockIdx.x; dbg[2] = (int)parity; }
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_LD32(addr, v)                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                        \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                        \
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"        \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),        \
+                   "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),      \
+                   "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),      \
+                   "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                           \
+                 : "r"(addr) : "memory")
+#define TMEM_LD16(addr, v)                                                                                        \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                        \
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                 \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), \
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),        \
+                   "=r"(v[15])                                                                                     \
+                 : "r"(addr) : "memory")
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// SiLU with ONE MUFU op per element: x*sigmoid(x) = 0.5x * (1 + tanh(0.5x)).
+__device__ __forceinline__ float silu_fast(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
+// K-major shared-memory matrix descriptor (sm_100 "version 1"), start address advanced by the caller
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo16, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);        // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(sbo16 & 0x3FFFu) << 32;          // stride byte offset: 8 rows * swizzle width
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)(layout_type & 7u) << 61;
+    return d;
+}
+
+// epilogue for NC columns held in v[] (fp32 bit patterns), columns [c0, c0+NC) of the CTA tile
+template <int NC>
+__device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, bool valid, long long pix, int n) {
+    float f[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) f[i] = __uint_as_float(v[i]);
+    if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < NC; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+        }
+    }
+    if (p.act == YRE_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) f[i] = silu_fast(f[i]);
+    }
+    if (!valid) return;
+    if (p.res) {
+        if (p.res_f32) {
+            const float* r = reinterpret_cast<const float*>(p.res) + pix * p.res_ctot + p.res_coff + n;
+#pragma unroll
+            for (int i = 0; i < NC; i += 4) {
+                const float4 r4 = *reinterpret_cast<const float4*>(r + i);
+                f[i] += r4.x; f[i + 1] += r4.y; f[i + 2] += r4.z; f[i + 3] += r4.w;
+            }
+        } else {
+            const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ctot + p.res_coff + n;
+#pragma unroll
+            for (int i = 0; i < NC; i += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(r + i);
+                f[i + 0] += __uint_as_float(u.x << 16); f[i + 1] += __uint_as_float(u.x & 0xffff0000u);
+                f[i + 2] += __uint_as_float(u.y << 16); f[i + 3] += __uint_as_float(u.y & 0xffff0000u);
+                f[i + 4] += __uint_as_float(u.z << 16); f[i + 5] += __uint_as_float(u.z & 0xffff0000u);
+                f[i + 6] += __uint_as_float(u.w << 16); f[i + 7] += __uint_as_float(u.w & 0xffff0000u);
+            }
+        }
+    }
+    if (p.y_f32) {
+        float* o = reinterpret_cast<float*>(p.y) + pix * p.y_ctot + p.y_coff + n;
+#pragma unroll
+        for (int i = 0; i < NC; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+    } else {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.y) + pix * p.y_ctot + p.y_coff + n;
+#pragma unroll
+        for (int i = 0; i < NC; i += 8) {
+            uint4 u;
+            u.x = pack_bf16x2(f[i], f[i + 1]); u.y = pack_bf16x2(f[i + 2], f[i + 3]);
+            u.z = pack_bf16x2(f[i + 4], f[i + 5]); u.w = pack_bf16x2(f[i + 6], f[i + 7]);
+            *reinterpret_cast<uint4*>(o + i) = u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    const uint32_t bar_base = sbase + (uint32_t)p.stages * stage_bytes;
+    // barrier i at bar_base + 8*i : full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4)
+    const uint32_t S = (uint32_t)p.stages;
+    const uint32_t tmem_slot = bar_base + 8u * (2u * S + 4u);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t i = 0; i < S; ++i) { mbar_init(bar_base + 8u * i, 1); mbar_init(bar_base + 8u * (S + i), 1); }
+        for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_base + 8u * (2u * S + i), 1); mbar_init(bar_base + 8u * (2u * S + 2u + i), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int kiters = p.taps * p.kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ================= TMA producer =================
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int nt = t % p.tiles_n; int mt = t / p.tiles_n;
+                const int xt = mt % p.tiles_x; mt /= p.tiles_x;
+                const int yt = mt % p.tiles_y; const int bt = mt / p.tiles_y;
+                const int x0 = xt * p.tw, y0 = yt * p.th, b0 = bt * p.tb, n0 = nt * p.block_n;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    int dx = 0, dy = 0, plane = 0;
+                    if (p.taps == 9) {
+                        const int ky = tap / 3, kx = tap % 3;
+                        if (p.phase4) {   // input row 2*oy + ky - 1  ->  parity (ky != 1), plane row oy - (ky == 0)
+                            plane = ((ky != 1) << 1) | (kx != 1);
+                            dy = (ky == 0) ? -1 : 0; dx = (kx == 0) ? -1 : 0;
+                        } else { dy = ky - 1; dx = kx - 1; }
+                    }
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (S + stage);
+                        mbar_wait(empty, phase ^ 1u, p.dbg, 1);
+                        mbar_expect_tx(full, stage_bytes);
+                        const uint32_t sa = sbase + stage * stage_bytes, sb = sa + p.a_bytes;
+                        const int c = p.x_coff + kc * p.block_k;
+                        if (p.phase4) tma_load_5d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
+                        else tma_load_4d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0);
+                        tma_load_2d(sb, &tmB, full, tap * p.Cin + kc * p.block_k, n0);
+                        if (++stage == S) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ================= MMA issuer =================
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            const int ksteps = p.block_k / 16;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 2u + acc);
+                mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                for (int it = 0; it < kiters; ++it) {
+                    const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (S + stage);
+                    mbar_wait(full, phase, p.dbg, 3);
+                    tc_fence_after();
+                    const uint32_t sa = sbase + stage * stage_bytes, sb = sa + p.a_bytes;
+                    const uint64_t da = make_smem_desc(sa, p.sbo16, p.layout_type);
+                    const uint64_t db = make_smem_desc(sb, p.sbo16, p.layout_type);
+                    for (int k = 0; k < ksteps; ++k) {
+                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (it | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty);                       // frees the smem stage when these MMAs retire
+                    if (it == kiters - 1) umma_commit(tfull); // accumulator complete -> epilogue
+                    if (++stage == S) { stage = 0; phase ^= 1u; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int ew = warp & 3;
+        const int row = ew * 32 + lane;
+        const int patch = p.tw * p.th;
+        const int bi = row / patch, rem = row % patch, yy = rem / p.tw, xx = rem % p.tw;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            const int nt = t % p.tiles_n; int mt = t / p.tiles_n;
+            const int xt = mt % p.tiles_x; mt /= p.tiles_x;
+            const int yt = mt % p.tiles_y; const int bt = mt / p.tiles_y;
+            const int x = xt * p.tw + xx, y = yt * p.th + yy, b = bt * p.tb + bi, n0 = nt * p.block_n;
+            const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+            const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+            const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 2u + acc);
+            mbar_wait(tfull, acc_phase, p.dbg, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_STRIDE;
+            int c = 0;
+            for (; c + 32 <= p.block_n; c += 32) {
+                uint32_t v[32];
+                TMEM_LD32(taddr + (uint32_t)c, v);
+                tmem_ld_wait();
+                epilogue_store<32>(p, v, valid, pix, n0 + c);
+            }
+            if (c < p.block_n) {   // block_n % 32 == 16
+                uint32_t v[16];
+                TMEM_LD16(taddr + (uint32_t)c, v);
+                tmem_ld_wait();
+                epilogue_store<16>(p, v, valid, pix, n0 + c);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct ConvTcPlan {
+    CUtensorMap tmA, tmB;
+    TcParams p;
+    int grid;
+    size_t smem;
+};
+
+int conv_tc_eligible(const yre_conv_desc& d, char* why, size_t n) {
+#define NOPE(msg) do { if (why && n) snprintf(why, n, "%s", msg); return 0; } while (0)
+    if (d.x.dtype != YRE_BF16) NOPE("input must be bf16");
+    if (d.y.layout != YRE_NHWC) NOPE("output must be NHWC");
+    if (d.k != 1 && d.k != 3) NOPE("kernel must be 1x1 or 3x3");
+    if (d.stride == 2 && !(d.k == 3 && d.x.layout == YRE_PHASE4)) NOPE("stride-2 needs a 3x3 kernel on a PHASE4 input");
+    if (d.stride == 1 && d.x.layout != YRE_NHWC) NOPE("stride-1 needs an NHWC input");
+    if (d.x.C % 32 || d.x.c_off % 8 || d.x.C_total % 8) NOPE("Cin must be a multiple of 32 (window 16-byte aligned)");
+    if (d.y.C % 16) NOPE("Cout must be a multiple of 16");
+    const int yal = d.y.dtype == YRE_F32 ? 4 : 8;
+    if (d.y.c_off % yal || d.y.C_total % yal) NOPE("output window must be 16-byte aligned");
+    if (d.res.ptr) {
+        const int ral = d.res.dtype == YRE_F32 ? 4 : 8;
+        if (d.res.layout != YRE_NHWC || d.res.c_off % ral || d.res.C_total % ral) NOPE("residual must be an aligned NHWC window");
+    }
+    if ((reinterpret_cast<uintptr_t>(d.x.ptr) & 127) || (reinterpret_cast<uintptr_t>(d.w) & 127)) NOPE("x and w must be 128-byte aligned");
+    if (d.bias && (reinterpret_cast<uintptr_t>(d.bias) & 15)) NOPE("bias must be 16-byte aligned");
+    if (!get_encode()) NOPE("cuTensorMapEncodeTiled unavailable");
+    return 1;
+#undef NOPE
+}
+
+int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: cuTensorMapEncodeTiled unavailable");
+    ConvTcPlan* pl = new ConvTcPlan();
+    memset(pl, 0, sizeof(*pl));
+    TcParams& p = pl->p;
+    const int Cin = d.x.C, Cout = d.y.C, Ho = d.y.H, Wo = d.y.W, B = d.y.B;
+    p.Ho = Ho; p.Wo = Wo; p.B = B; p.Cin = Cin; p.x_coff = d.x.c_off;
+    p.taps = d.k * d.k;
+    p.phase4 = d.stride == 2;
+    p.block_k = (Cin % 64 == 0) ? 64 : 32;
+    p.kchunks = Cin / p.block_k;
+    p.layout_type = p.block_k == 64 ? 2u : 4u;
+    p.sbo16 = (uint32_t)(8 * p.block_k * 2) >> 4;
+
+    // ---- M tiling: (tw, th, tb) powers of two with product 128 minimising the tile count ----
+    long long best = -1; int btw = 128, bth = 1, btb = 1;
+    for (int tw = 128; tw >= 1; tw >>= 1)
+        for (int th = 128 / tw; th >= 1; th >>= 1) {
+            const int tb = 128 / (tw * th);
+            const long long tiles = (long long)yre_cdiv(Wo, tw) * yre_cdiv(Ho, th) * yre_cdiv(B, tb);
+            if (best < 0 || tiles < best) { best = tiles; btw = tw; bth = th; btb = tb; }
+        }
+    p.tw = btw; p.th = bth; p.tb = btb;
+    p.tiles_x = yre_cdiv(Wo, btw); p.tiles_y = yre_cdiv(Ho, bth); p.tiles_b = yre_cdiv(B, btb);
+    const long long mtiles = best;
+
+    // ---- N tiling ----
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int bn = 0;
+    for (int c = 256; c >= 16; c -= 16) if (Cout % c == 0) { bn = c; break; }
+    // keep the machine busy: halve N tiles while there are fewer tiles than SMs
+    while (bn >= 64 && bn % 32 == 0 && mtiles * (Cout / bn) < sms) bn /= 2;
+    const int force_bn = env_int("YRE_TC_BLOCK_N", 0);
+    if (force_bn >= 16 && force_bn <= 256 && force_bn % 16 == 0 && Cout % force_bn == 0) bn = force_bn;
+    p.block_n = bn;
+    p.tiles_n = Cout / bn;
+    p.num_tiles = (int)(mtiles * p.tiles_n);
+    p.a_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
+    p.b_bytes = (uint32_t)(bn * p.block_k * 2);
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    int stages = (int)((200u * 1024u) / stage_bytes);
+    if (stages > 8) stages = 8;
+    const int force_st = env_int("YRE_TC_STAGES", 0);
+    if (force_st >= 2 && force_st <= stages) stages = force_st;
+    if (stages < 2) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: tile does not fit shared memory"); }
+    p.stages = stages;
+    pl->smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 1024;
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    p.bias = d.bias; p.act = d.act;
+    p.y = d.y.ptr; p.y_f32 = d.y.dtype == YRE_F32; p.y_ctot = d.y.C_total; p.y_coff = d.y.c_off;
+    p.res = d.res.ptr; p.res_f32 = d.res.ptr ? d.res.dtype == YRE_F32 : 0;
+    p.res_ctot = d.res.ptr ? d.res.C_total : 0; p.res_coff = d.res.ptr ? d.res.c_off : 0;
+    p.dbg = nullptr;
+    pl->grid = p.num_tiles < sms ? p.num_tiles : sms;
+
+    // ---- tensor maps ----
+    const CUtensorMapSwizzle swz = p.block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r;
+    if (!p.phase4) {
+        cuuint64_t gdim[4] = {(cuuint64_t)d.x.C_total, (cuuint64_t)d.x.W, (cuuint64_t)d.x.H, (cuuint64_t)d.x.B};
+        cuuint64_t gstr[3] = {(cuuint64_t)d.x.C_total * 2, (cuuint64_t)d.x.W * d.x.C_total * 2, (cuuint64_t)d.x.H * d.x.W * d.x.C_total * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tb};
+        cuuint32_t est[4] = {1, 1, 1, 1};
+        r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.x.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t Hp = (cuuint64_t)(d.x.H + 1) / 2, Wp = (cuuint64_t)(d.x.W + 1) / 2, Ct = (cuuint64_t)d.x.C_total;
+        cuuint64_t gdim[5] = {Ct, Wp, Hp, (cuuint64_t)d.x.B, 4};
+        cuuint64_t gstr[4] = {Ct * 2, Wp * Ct * 2, Hp * Wp * Ct * 2, (cuuint64_t)d.x.B * Hp * Wp * Ct * 2};
+        cuuint32_t box[5] = {(cuuint32_t)p.block_k, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tb, 1};
+        cuuint32_t est[5] = {1, 1, 1, 1, 1};
+        r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d.x.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); }
+    {
+        const cuuint64_t K = (cuuint64_t)p.taps * Cin;
+        cuuint64_t gdim[2] = {K, (cuuint64_t)Cout};
+        cuuint64_t gstr[1] = {K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)bn};
+        cuuint32_t est[2] = {1, 1};
+        r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r); }
+    *out = pl;
+    return YRE_OK;
+}
+
+int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    conv_tc_kernel<<<pl->grid, NUM_THREADS, pl->smem, s>>>(pl->tmA, pl->tmB, pl->p);
+    YRE_LAUNCH_CHECK("conv_tc");
+    return YRE_OK;
+}
+
+void conv_tc_free(ConvTcPlan* p) { delete p; }
+
+int conv_tc_rebind(ConvTcPlan* pl, const void* old_ptr, void* new_ptr) {
+    int n = 0;
+    if (pl->p.y == old_ptr) { pl->p.y = new_ptr; ++n; }
+    if (pl->p.res == old_ptr) { pl->p.res = new_ptr; ++n; }
+    return n;
+}

@@ -1,0 +1,353 @@
+// K7: batched class-aware NMS, bit-exact with the reference.
+//
+//   reference: non_max_suppression           src/yolo/utils/nms.py:19-94
+//              torchvision.ops.nms via _nms   src/yolo/utils/nms.py:97-104
+//
+// Three launches for the whole batch (the reference loops over images in Python):
+//   nms_init    zero the per-image counters
+//   nms_filter  HBM-bound pass over pred[B][A][4+nc]: per-anchor first-max class, strict
+//               `conf > thr` (+ optional class filter), xywh->xyxy, per-image max coordinate,
+//               compaction of (score, anchor) sort keys
+//   nms_select  one CTA per image: bitonic sort of the 64-bit keys (== stable descending score
+//               sort, ties -> lower anchor first), then a chunked greedy scan: every chunk of
+//               CHUNK sorted candidates is tested against the boxes kept so far (<= max_det of
+//               them), an IoU bitmask is built inside the chunk, and a serial pass over the
+//               bitmask resolves it.  The scan stops as soon as max_det boxes are kept, which
+//               is exactly `keep[:max_det]` of the reference -- there is no pre-NMS top-k cap.
+//
+// Bit-exactness notes: every fp32 op is an explicitly rounded intrinsic (no FMA contraction);
+// the class offset is `float(cls) * (max_coord + 1)` then `box + offset` as two rounded ops
+// (nms.py:79-81); IoU is inter / ((area_i + area_j) - inter) in fp32, compared against the
+// threshold as a DOUBLE, as torchvision's CPU kernel does.
+#include "yre_common.cuh"
+
+namespace {
+
+constexpr int CHUNK = 512;            // == threads of nms_select
+constexpr int CW = CHUNK / 64;        // mask words per row
+constexpr int SMEM_KEYS = 8192;       // keys sorted in shared memory when they fit
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ unsigned f2ord(float f) {   // order-preserving float -> uint
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+struct NmsWs {           // carved out of the caller's workspace
+    u64* keys;           // [B][cap]
+    int* cls;            // [B][A]
+    int* count;          // [B]
+    unsigned* maxc;      // [B] (ordered-uint encoding)
+    int cap;
+};
+
+__host__ __device__ inline int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+__global__ void nms_init_kernel(int* count, unsigned* maxc, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) { count[i] = 0; maxc[i] = 0u; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// filter: one warp per 32 consecutive anchors of one image; rows are read as coalesced float4
+struct FilterParams {
+    const float* pred; int B, A, nc; float conf; const int* classes; int n_classes;
+    NmsWs ws;
+};
+
+__global__ void __launch_bounds__(128) nms_filter_kernel(const FilterParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n4 = (4 + p.nc) / 4;                 // float4 per row (nc % 4 == 0)
+    const int nparts = n4 - 1;
+    const int pitch = nparts | 1;                  // odd pitch: conflict-free per-lane rows
+    float* pv = reinterpret_cast<float*>(smraw) + (size_t)warp * 32 * pitch * 2;    // [32][pitch] best value
+    int* pi = reinterpret_cast<int*>(pv + 32 * pitch);                               // [32][pitch] best class
+
+    const int tiles = (p.A + 31) / 32;
+    const int wglobal = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (wglobal >= tiles * p.B) return;
+    const int b = wglobal / tiles, a0 = (wglobal % tiles) * 32;
+    const int na = min(32, p.A - a0);
+    const float4* base = reinterpret_cast<const float4*>(p.pred + ((size_t)b * p.A + a0) * (4 + p.nc));
+
+    for (int idx = lane; idx < na * n4; idx += 32) {
+        const int al = idx / n4, pos = idx % n4;
+        if (pos == 0) continue;
+        const float4 v = base[idx];
+        float best = v.x; int bi = 0;
+        if (v.y > best) { best = v.y; bi = 1; }
+        if (v.z > best) { best = v.z; bi = 2; }
+        if (v.w > best) { best = v.w; bi = 3; }
+        pv[al * pitch + pos - 1] = best;
+        pi[al * pitch + pos - 1] = (pos - 1) * 4 + bi;
+    }
+    __syncwarp();
+
+    bool cand = false;
+    float conf = 0.f; int cls = 0;
+    float x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+    if (lane < na) {
+        conf = pv[lane * pitch]; cls = pi[lane * pitch];
+        for (int q = 1; q < nparts; ++q) {
+            const float v = pv[lane * pitch + q];
+            if (v > conf) { conf = v; cls = pi[lane * pitch + q]; }     // strict > keeps the first max
+        }
+        cand = conf > p.conf;
+        if (cand && p.n_classes >= 0) {
+            bool ok = false;
+            for (int k = 0; k < p.n_classes; ++k) ok |= (p.classes[k] == cls);
+            cand = ok;
+        }
+        if (cand) {
+            const float4 bx = base[lane * n4];
+            const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);   // w/2, h/2 (exact)
+            x1 = __fsub_rn(bx.x, hw); y1 = __fsub_rn(bx.y, hh);
+            x2 = __fadd_rn(bx.x, hw); y2 = __fadd_rn(bx.y, hh);
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, cand);
+    if (ballot == 0u) return;
+    // per-image max coordinate over candidate boxes
+    unsigned mo = cand ? max(max(f2ord(x1), f2ord(y1)), max(f2ord(x2), f2ord(y2))) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mo = max(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+    int slot0 = 0;
+    if (lane == 0) {
+        atomicMax(p.ws.maxc + b, mo);
+        slot0 = atomicAdd(p.ws.count + b, __popc(ballot));
+    }
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    if (cand) {
+        const int slot = slot0 + __popc(ballot & ((1u << lane) - 1u));
+        const int a = a0 + lane;
+        p.ws.keys[(size_t)b * p.ws.cap + slot] = ((u64)(~f2ord(conf)) << 32) | (unsigned)a;
+        p.ws.cls[(size_t)b * p.A + a] = cls;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct SelectParams {
+    const float* pred; int B, A, nc; double iou; int max_det, agnostic;
+    NmsWs ws;
+    float* out; int* counts; long long* keep_anchor;
+    int keys_in_smem;     // SMEM_KEYS or 0
+};
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const float4 b, const float ab, const double thr) {
+    const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+    const float inter = __fmul_rn(w, h);
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+    return (double)iou > thr;
+}
+
+__device__ void bitonic_sort(u64* d, int np) {
+    for (int k = 2; k <= np; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < (np >> 1); i += blockDim.x) {
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const int hi = lo | j;
+                const bool asc = (lo & k) == 0;
+                const u64 a = d[lo], b = d[hi];
+                if ((a > b) == asc) { d[lo] = b; d[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    // carve shared memory
+    float4* cbox = reinterpret_cast<float4*>(smraw);                 // [CHUNK] offset boxes
+    float4* ubox = cbox + CHUNK;                                     // [CHUNK] plain boxes
+    float4* kbox = ubox + CHUNK;                                     // [max_det] kept offset boxes
+    u64* mask = reinterpret_cast<u64*>(kbox + p.max_det);            // [CHUNK][CW]
+    u64* skeys = mask + (size_t)CHUNK * CW;                          // [keys_in_smem]
+    float* carea = reinterpret_cast<float*>(skeys + p.keys_in_smem); // [CHUNK]
+    float* cconf = carea + CHUNK;                                    // [CHUNK]
+    float* karea = cconf + CHUNK;                                    // [max_det]
+    int* ccls = reinterpret_cast<int*>(karea + p.max_det);           // [CHUNK]
+    int* canc = ccls + CHUNK;                                        // [CHUNK]
+    int* kpos = canc + CHUNK;                                        // [CHUNK] chunk positions kept this round
+    unsigned* alive_w = reinterpret_cast<unsigned*>(kpos + CHUNK);   // [CHUNK/32]
+    __shared__ int s_newkept;
+
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = min(p.ws.count[b], p.A);
+    if (n == 0) { if (tid == 0) p.counts[b] = 0; return; }
+    const int np = pow2ceil(n);
+    u64* gkeys = p.ws.keys + (size_t)b * p.ws.cap;
+    u64* keys;
+    if (np <= p.keys_in_smem) {
+        for (int i = tid; i < np; i += blockDim.x) skeys[i] = i < n ? gkeys[i] : ~0ull;
+        keys = skeys;
+    } else {
+        for (int i = n + tid; i < np; i += blockDim.x) gkeys[i] = ~0ull;
+        keys = gkeys;
+    }
+    __syncthreads();
+    bitonic_sort(keys, np);
+
+    const float scale = __fadd_rn(ord2f(p.ws.maxc[b]), 1.0f);
+    const int rowf = 4 + p.nc;
+    int kept = 0;
+    for (int c0 = 0; c0 < n && kept < p.max_det; c0 += CHUNK) {
+        const int cnt = min(CHUNK, n - c0);
+        // ---- 1. load this chunk's candidates ----
+        bool alive = tid < cnt;
+        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
+        float marea = 0.f;
+        if (alive) {
+            const u64 key = keys[c0 + tid];
+            const int a = (int)(unsigned)(key & 0xffffffffu);
+            const float conf = ord2f(~(unsigned)(key >> 32));
+            const int cls = p.ws.cls[(size_t)b * p.A + a];
+            const float* row = p.pred + ((size_t)b * p.A + a) * rowf;
+            const float4 bx = *reinterpret_cast<const float4*>(row);
+            const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);
+            float4 u;
+            u.x = __fsub_rn(bx.x, hw); u.y = __fsub_rn(bx.y, hh); u.z = __fadd_rn(bx.x, hw); u.w = __fadd_rn(bx.y, hh);
+            if (p.agnostic) mine = u;
+            else {
+                const float off = __fmul_rn(__int2float_rn(cls), scale);
+                mine.x = __fadd_rn(u.x, off); mine.y = __fadd_rn(u.y, off);
+                mine.z = __fadd_rn(u.z, off); mine.w = __fadd_rn(u.w, off);
+            }
+            marea = __fmul_rn(__fsub_rn(mine.z, mine.x), __fsub_rn(mine.w, mine.y));
+            ubox[tid] = u; cbox[tid] = mine; carea[tid] = marea; cconf[tid] = conf; ccls[tid] = cls; canc[tid] = a;
+            // ---- 2. against everything kept by earlier chunks ----
+            for (int k = 0; k < kept; ++k)
+                if (iou_gt(kbox[k], karea[k], mine, marea, p.iou)) { alive = false; break; }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        if ((tid & 31) == 0) alive_w[tid >> 5] = bal;
+        __syncthreads();
+        // ---- 3. in-chunk suppression bitmask (row i: later boxes j>i it would suppress) ----
+        if (alive) {
+            for (int w = 0; w < CW; ++w) {
+                u64 bits = 0ull;
+                const int j0 = w * 64;
+                if (j0 + 63 > tid && j0 < cnt) {
+                    const int jend = min(64, cnt - j0);
+                    for (int jj = max(0, tid + 1 - j0); jj < jend; ++jj) {
+                        const int j = j0 + jj;
+                        if (!((alive_w[j >> 5] >> (j & 31)) & 1u)) continue;
+                        if (iou_gt(mine, marea, cbox[j], carea[j], p.iou)) bits |= 1ull << jj;
+                    }
+                }
+                mask[(size_t)tid * CW + w] = bits;
+            }
+        }
+        __syncthreads();
+        // ---- 4. serial resolution of the chunk ----
+        if (tid == 0) {
+            // `removed` lives in registers: the word loop is fully unrolled so every index is static
+            u64 removed[CW];
+#pragma unroll
+            for (int w = 0; w < CW; ++w) removed[w] = 0ull;
+            int nk = 0;
+            bool full = false;
+#pragma unroll
+            for (int w = 0; w < CW; ++w) {
+                if (full || w * 64 >= cnt) continue;
+                const u64 al = (u64)alive_w[2 * w] | ((u64)alive_w[2 * w + 1] << 32);
+                const int lim = min(64, cnt - w * 64);
+                for (int jj = 0; jj < lim; ++jj) {
+                    if (!((al >> jj) & 1ull) || ((removed[w] >> jj) & 1ull)) continue;
+                    const int i = w * 64 + jj;
+                    kpos[nk++] = i;
+                    if (kept + nk >= p.max_det) { full = true; break; }
+#pragma unroll
+                    for (int v = 0; v < CW; ++v)
+                        if (v >= w) removed[v] |= mask[(size_t)i * CW + v];
+                }
+            }
+            s_newkept = nk;
+        }
+        __syncthreads();
+        // ---- 5. publish the newly kept boxes ----
+        const int nk = s_newkept;
+        for (int q = tid; q < nk; q += blockDim.x) {
+            const int i = kpos[q], k = kept + q;
+            kbox[k] = cbox[i]; karea[k] = carea[i];
+            float* o = p.out + ((size_t)b * p.max_det + k) * 6;
+            const float4 u = ubox[i];
+            o[0] = u.x; o[1] = u.y; o[2] = u.z; o[3] = u.w; o[4] = cconf[i]; o[5] = __int2float_rn(ccls[i]);
+            p.keep_anchor[(size_t)b * p.max_det + k] = canc[i];
+        }
+        kept += nk;
+        __syncthreads();
+    }
+    if (tid == 0) p.counts[b] = kept;
+}
+
+size_t select_smem_bytes(int max_det, int keys_in_smem) {
+    return sizeof(float4) * (2 * CHUNK + (size_t)max_det) + sizeof(u64) * ((size_t)CHUNK * CW + keys_in_smem) +
+           sizeof(float) * (2 * CHUNK + (size_t)max_det) + sizeof(int) * (3 * CHUNK) + sizeof(unsigned) * (CHUNK / 32) + 64;
+}
+
+NmsWs carve(void* ws, int B, int A) {
+    NmsWs w;
+    w.cap = pow2ceil(A);
+    unsigned char* p = reinterpret_cast<unsigned char*>(ws);
+    w.keys = reinterpret_cast<u64*>(p); p += sizeof(u64) * (size_t)B * w.cap;
+    w.cls = reinterpret_cast<int*>(p); p += sizeof(int) * (size_t)B * A;
+    w.count = reinterpret_cast<int*>(p); p += sizeof(int) * (size_t)B;
+    w.maxc = reinterpret_cast<unsigned*>(p);
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t yre_nms_workspace_bytes(int32_t B, int32_t A) {
+    if (B <= 0 || A <= 0) return 0;
+    return sizeof(u64) * (size_t)B * pow2ceil(A) + sizeof(int) * (size_t)B * A + 2 * sizeof(int) * (size_t)B + 256;
+}
+
+int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
+    if (!d.pred || !d.out || !d.counts || !d.keep_anchor || !d.workspace) YRE_FAIL(YRE_EINVAL, "nms: null pointer");
+    if (d.B <= 0 || d.A <= 0 || d.nc <= 0) YRE_FAIL(YRE_EINVAL, "nms: bad extent B=%d A=%d nc=%d", d.B, d.A, d.nc);
+    if (d.nc % 4) YRE_FAIL(YRE_EUNSUPPORTED, "nms: nc=%d must be a multiple of 4", d.nc);
+    if (d.max_det <= 0 || d.max_det > 4096) YRE_FAIL(YRE_EUNSUPPORTED, "nms: max_det=%d (supported 1..4096)", d.max_det);
+    if (d.workspace_bytes < yre_nms_workspace_bytes(d.B, d.A)) YRE_FAIL(YRE_EINVAL, "nms: workspace too small");
+    if (d.n_classes > 0 && !d.classes) YRE_FAIL(YRE_EINVAL, "nms: classes pointer missing");
+    if ((reinterpret_cast<uintptr_t>(d.pred) & 15) || (reinterpret_cast<uintptr_t>(d.workspace) & 15))
+        YRE_FAIL(YRE_EINVAL, "nms: pred/workspace must be 16-byte aligned");
+    NmsWs ws = carve(d.workspace, d.B, d.A);
+
+    nms_init_kernel<<<yre_cdiv(d.B, 256), 256, 0, s>>>(ws.count, ws.maxc, d.B);
+    YRE_LAUNCH_CHECK("nms_init");
+
+    FilterParams fp;
+    fp.pred = d.pred; fp.B = d.B; fp.A = d.A; fp.nc = d.nc; fp.conf = d.conf_thres;
+    fp.classes = d.classes; fp.n_classes = d.n_classes; fp.ws = ws;
+    const size_t per_warp = (size_t)32 * ((d.nc / 4) | 1) * 8;
+    int warps = 4;
+    while (warps > 1 && per_warp * warps > 40 * 1024) warps >>= 1;
+    if (per_warp * warps > 48 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "nms: nc=%d too large", d.nc);
+    const int tiles = yre_cdiv(d.A, 32) * d.B;
+    nms_filter_kernel<<<yre_cdiv(tiles, warps), warps * 32, per_warp * warps, s>>>(fp);
+    YRE_LAUNCH_CHECK("nms_filter");
+
+    SelectParams sp;
+    sp.pred = d.pred; sp.B = d.B; sp.A = d.A; sp.nc = d.nc; sp.iou = d.iou_thres; sp.max_det = d.max_det;
+    sp.agnostic = d.agnostic; sp.ws = ws; sp.out = d.out; sp.counts = d.counts;
+    sp.keep_anchor = reinterpret_cast<long long*>(d.keep_anchor);
+    sp.keys_in_smem = SMEM_KEYS;
+    const size_t smem = select_smem_bytes(d.max_det, SMEM_KEYS);
+    static bool attr_done = false;
+    if (!attr_done) {
+        YRE_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    if (smem > 200 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "nms: shared memory budget exceeded");
+    nms_select_kernel<<<d.B, CHUNK, smem, s>>>(sp);
+    YRE_LAUNCH_CHECK("nms_select");
+    return YRE_OK;
+}

@@ -1,0 +1,13 @@
+"""yolo_b200 -- B200-native (sm_100a) implementation of yolo-re's detection inference hot path.
+
+Public names mirror the reference package (src/yolo/__init__.py:3-20) for the path in scope:
+``YOLO`` (``from_yaml`` / ``from_config`` / ``forward`` / ``state_dict``) and ``non_max_suppression``.
+"""
+from ._lib import YreError, lib
+from .engine import precision
+from .model import BLOCKS, YOLO, ModelConfig, build_layers, parse_yaml
+from .nms import nms_raw, non_max_suppression
+
+__version__ = "0.1.0"
+__all__ = ["YOLO", "non_max_suppression", "nms_raw", "precision", "YreError", "lib", "ModelConfig", "parse_yaml",
+           "build_layers", "BLOCKS"]
