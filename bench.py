@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default 64 = the metric's config)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-op", default="", help="write a per-launch CSV (kernel, shape, ms, TFLOP/s) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -287,6 +288,11 @@ def main():
         torch.cuda.synchronize(dev)
         for i in range(n_ops):
             per_op[i] += evs[i].elapsed_time(evs[i + 1]) / reps
+    if args.per_op:
+        with open(args.per_op, "w") as f:
+            f.write("op,kernel,shape,ms,gflop,tflops\n")
+            for i, ((name, fl), tms, desc) in enumerate(zip(table, per_op, plan.op_descriptions())):
+                f.write(f"{i},{name},{desc},{tms:.5f},{fl / 1e9:.3f},{(fl / (tms / 1e3) / 1e12) if tms > 0 else 0:.1f}\n")
     peak_tf, peak_gbs, peak_src = peaks()
     fam = {}
     for (name, fl), tms in zip(table, per_op):

@@ -58,12 +58,18 @@ def test_fp32_end_to_end_vs_oracle_and_nms(gelan_c, size, batch):
     nodes, nc, sd = gelan_c
     x = G.fractal(batch, size, torch.Generator().manual_seed(size))
     y_ref, raws_ref = G.forward(nodes, nc, sd, x)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    y64, _ = G.forward(nodes, nc, sd64, x.double())               # the reference graph in fp64 = ground truth
+    floor_box = (y_ref[:, :4].double() - y64[:, :4]).abs().max().item()      # the reference's own fp32 noise
+    floor_sc = (y_ref[:, 4:].double() - y64[:, 4:]).abs().max().item()
     m = build("gelan-c", sd, "fp32")
     y, raws = m(x.to(DEV))
     A = sum((size // s) ** 2 for s in (8, 16, 32))
     assert y.shape == (batch, 84, A) and [tuple(r.shape) for r in raws] == [(batch, 144, size // s, size // s) for s in (8, 16, 32)]
-    assert (y[:, :4].cpu() - y_ref[:, :4]).abs().max() <= max(1e-4 * size, 2e-2)
-    assert (y[:, 4:].cpu() - y_ref[:, 4:]).abs().max() <= 2e-4
+    dbox = (y[:, :4].cpu().double() - y64[:, :4]).abs().max().item()
+    dsc = (y[:, 4:].cpu().double() - y64[:, 4:]).abs().max().item()
+    print(f"{size}x{size} B{batch}: ours-vs-fp64 |dbox|={dbox:.3e}px |dscore|={dsc:.3e}; reference fp32-vs-fp64 floor {floor_box:.3e}px {floor_sc:.3e}")
+    assert dbox <= max(1e-4 * size, 3 * floor_box) and dsc <= max(1e-4, 3 * floor_sc)
     pred = y.permute(0, 2, 1).contiguous()                       # what callers do (scripts/detect.py:247)
     dets = yolo_b200.non_max_suppression(pred, 0.25, 0.45)
     ref = N.non_max_suppression(pred.cpu(), 0.25, 0.45)
@@ -99,9 +105,14 @@ def test_bf16_end_to_end_drift_reported(gelan_c):
     assert plan.num_tcgen05 >= 120, f"only {plan.num_tcgen05} convs ran on tcgen05"
     dbox = (y[:, :4].cpu() - y_ref[:, :4]).abs()
     dsc = (y[:, 4:].cpu() - y_ref[:, 4:]).abs()
+    # yardstick: the reference graph itself run in bf16 (model.bfloat16() semantics: three roundings per Conv)
+    sdb = {k: (v.bfloat16() if v.is_floating_point() else v) for k, v in sd.items()}
+    yb, _ = G.forward(nodes, nc, sdb, x.bfloat16())
+    rbox, rsc = (yb[:, :4].float() - y_ref[:, :4]).abs(), (yb[:, 4:].float() - y_ref[:, 4:]).abs()
     print(f"bf16 e2e drift: box mean {dbox.mean():.3f}px max {dbox.max():.2f}px; score mean {dsc.mean():.2e} max {dsc.max():.2e}; "
+          f"reference-in-bf16: box mean {rbox.mean():.3f}px, score mean {rsc.mean():.2e}; "
           f"tcgen05 convs {plan.num_tcgen05}/{plan.num_launches} launches")
-    assert dbox.mean() < 1.0 and dsc.mean() < 5e-3
+    assert dbox.mean() <= 1.25 * rbox.mean() + 0.05 and dsc.mean() <= 1.25 * rsc.mean() + 1e-4
     dets = yolo_b200.non_max_suppression(y.permute(0, 2, 1), 0.25, 0.45)
     ref = N.non_max_suppression(y.permute(0, 2, 1).contiguous().cpu(), 0.25, 0.45)
     for a, b in zip(dets, ref):

@@ -13,35 +13,35 @@ namespace {
 // it emits the four average-map pixels (2oy+py, 2ox+px) -- i.e. one cell of each parity plane;
 // for the high half it emits max over average rows/cols 2o-1..2o+1.
 template <typename T>
-__global__ void __launch_bounds__(256) adown_prepool_kernel(DView x, DView lo, DView hi, int Ho, int Wo, int half) {
-    const int groups = x.C / 8;
+__global__ void __launch_bounds__(256, 2) adown_prepool_kernel(DView x, DView lo, DView hi, int Ho, int Wo, int half) {
+    // blockIdx.y selects the channel half, so the (very different) low/high paths never share a warp
+    const int hgroups = half / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)x.B * Ho * Wo * groups;
+    const long long total = (long long)x.B * Ho * Wo * hgroups;
     if (idx >= total) return;
-    const int g = (int)(idx % groups);
-    long long t = idx / groups;
+    const int g = (int)(idx % hgroups);
+    long long t = idx / hgroups;
     const int ox = (int)(t % Wo); t /= Wo;
     const int oy = (int)(t % Ho);
     const int b = (int)(t / Ho);
-    const int c = g * 8;
+    const int c = g * 8 + (blockIdx.y ? half : 0);
     const int Ha = x.H - 1, Wa = x.W - 1;          // average-map extent
 
     if (c < half) {
-        // x rows 2oy..2oy+2, cols 2ox..2ox+2
-        float v[3][3][8];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
+        // x rows 2oy..2oy+2, cols 2ox..2ox+2, streamed two rows at a time
+        float ra[3][8], rb[3][8];
+        auto load_row = [&](int iy, float (*r)[8]) {
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                const int iy = 2 * oy + r, ix = 2 * ox + q;
-                if (iy < x.H && ix < x.W) ld8<T>(x.ptr, dview_pix(x, b, iy, ix) + c, v[r][q]);
+                const int ix = 2 * ox + q;
+                if (iy < x.H && ix < x.W) ld8<T>(x.ptr, dview_pix(x, b, iy, ix) + c, r[q]);
                 else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[r][q][e] = 0.f;
+                    for (int e = 0; e < 8; ++e) r[q][e] = 0.f;
                 }
             }
-#pragma unroll
-        for (int py = 0; py < 2; ++py)
+        };
+        auto emit = [&](int py, float (*top)[8], float (*bot)[8]) {
 #pragma unroll
             for (int px = 0; px < 2; ++px) {
                 const int ay = 2 * oy + py, ax = 2 * ox + px;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) adown_prepool_kernel(DView x, DView lo, D
                 const bool ok = ay < Ha && ax < Wa;
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
-                    o[e] = ok ? (((v[py][px][e] + v[py][px + 1][e]) + v[py + 1][px][e]) + v[py + 1][px + 1][e]) * 0.25f : 0.f;
+                    o[e] = ok ? (((top[px][e] + top[px + 1][e]) + bot[px][e]) + bot[px + 1][e]) * 0.25f : 0.f;
                 if (lo.layout == YRE_PHASE4) {
                     // every cell of every parity plane is written (zeros where no source pixel exists)
                     if ((ay >> 1) < lo.Hp && (ax >> 1) < lo.Wp) st8<T>(lo.ptr, dview_pix(lo, b, ay, ax) + c, o);
@@ -57,6 +57,12 @@ __global__ void __launch_bounds__(256) adown_prepool_kernel(DView x, DView lo, D
                     st8<T>(lo.ptr, dview_pix(lo, b, ay, ax) + c, o);
                 }
             }
+        };
+        load_row(2 * oy, ra);
+        load_row(2 * oy + 1, rb);
+        emit(0, ra, rb);
+        load_row(2 * oy + 2, ra);
+        emit(1, rb, ra);
     } else {
         float m[8];
 #pragma unroll
@@ -268,8 +274,8 @@ int launch_adown_prepool(const yre_view& x, const yre_view& lo, const yre_view& 
     // the thread grid walks ceil((H-1)/2) x ceil((W-1)/2) cells, which covers both outputs
     const int Gy = (x.H - 1 + 1) / 2, Gx = (x.W - 1 + 1) / 2;
     if (Gy < Ho || Gx < Wo) YRE_FAIL(YRE_EINVAL, "adown: grid smaller than the pooled output");
-    const long long total = (long long)x.B * Gy * Gx * (x.C / 8);
-    dim3 grid(yre_cdiv(total, 256));
+    const long long total = (long long)x.B * Gy * Gx * (half / 8);
+    dim3 grid(yre_cdiv(total, 256), 2);
     // NB: kernel indexes its cell grid with (Ho,Wo) = (Gy,Gx); cells beyond hi's extent never
     // occur because Gy==Ho, Gx==Wo for every H,W >= 2.
     if (Gy != Ho || Gx != Wo) YRE_FAIL(YRE_EUNSUPPORTED, "adown: H=%d W=%d", x.H, x.W);

@@ -2,9 +2,9 @@
 //
 //   y = act(conv(x, w) + bias)          -- reference: layers.stem1, src/yolo/blocks/conv.py:88-89
 //
-// HBM-bound (AI ~ 23 FLOP/B): one thread owns one output pixel, keeps its 3x3xCin patch in
-// registers, and walks the output channels 16 at a time with the folded weights broadcast from
-// shared memory.  Output is written channels-last (optionally as the 4 parity planes the
+// HBM-bound (AI ~ 23 FLOP/B): one thread owns 4 consecutive output pixels of a row, keeps their
+// 3 x (4*stride+1) x Cin input patch in registers, and walks the output channels 16 at a time with
+// the folded weights broadcast from shared memory (one weight read feeds 4 pixels).  Output is written channels-last (optionally as the 4 parity planes the
 // stride-2 tcgen05 conv that follows wants), 32 B per store.
 #include "yre_common.cuh"
 
@@ -18,10 +18,13 @@ struct StemParams {
     int B, Cin, H, W, Ho, Wo, Cout, stride, act;
 };
 
-template <typename TOut, int CIN>
+constexpr int PX = 4;   // output pixels per thread (consecutive in x): weights are read once per 4 pixels
+
+template <typename TOut, int CIN, int STRIDE>
 __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
     extern __shared__ __align__(16) float sw[];               // [9*CIN][Cout] + bias[Cout]
-    const int K = 9 * CIN;
+    constexpr int K = 9 * CIN;
+    constexpr int NCOL = (PX - 1) * STRIDE + 3;
     for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
         const int co = i / K, kk = i % K;       // global order [co][tap][ci]
         sw[kk * p.Cout + co] = p.w[i];
@@ -30,49 +33,69 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
     for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sb[i] = p.bias ? p.bias[i] : 0.f;
     __syncthreads();
 
-    const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)p.B * p.Ho * p.Wo;
-    if (pix >= total) return;
-    const int ox = (int)(pix % p.Wo);
-    const long long t = pix / p.Wo;
+    const int xg = (p.Wo + PX - 1) / PX;                      // pixel groups per output row
+    const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.B * p.Ho * xg;
+    if (gidx >= total) return;
+    const int ox0 = (int)(gidx % xg) * PX;
+    const long long t = gidx / xg;
     const int oy = (int)(t % p.Ho), b = (int)(t / p.Ho);
 
-    float in[9 * CIN];
+    float in[3][NCOL][CIN];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+    for (int dy = 0; dy < 3; ++dy) {
+        const int iy = oy * STRIDE + dy - 1;
+        const bool rok = iy >= 0 && iy < p.H;
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int iy = oy * p.stride + dy - 1, ix = ox * p.stride + dx - 1;
-            const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+        for (int cx = 0; cx < NCOL; ++cx) {
+            const int ix = ox0 * STRIDE + cx - 1;
+            const bool ok = rok && ix >= 0 && ix < p.W;
 #pragma unroll
             for (int ci = 0; ci < CIN; ++ci)
-                in[(dy * 3 + dx) * CIN + ci] = ok ? __ldg(p.x + (((long long)b * CIN + ci) * p.H + iy) * p.W + ix) : 0.f;
+                in[dy][cx][ci] = ok ? __ldg(p.x + (((long long)b * CIN + ci) * p.H + iy) * p.W + ix) : 0.f;
         }
+    }
 
-    const long long obase = dview_pix(p.y, b, oy, ox);
+    long long obase[PX];
+#pragma unroll
+    for (int q = 0; q < PX; ++q) obase[q] = (ox0 + q < p.Wo) ? dview_pix(p.y, b, oy, ox0 + q) : -1;
+
     for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-        float acc[16];
+        float acc[PX][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = sb[c0 + j];
+        for (int q = 0; q < PX; ++q)
 #pragma unroll
-        for (int kk = 0; kk < 9 * CIN; ++kk) {
-            const float v = in[kk];
-            const float4* wr = reinterpret_cast<const float4*>(sw + kk * p.Cout + c0);
+            for (int j = 0; j < 16; ++j) acc[q][j] = sb[c0 + j];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 w4 = wr[q];
-                acc[q * 4 + 0] = fmaf(v, w4.x, acc[q * 4 + 0]);
-                acc[q * 4 + 1] = fmaf(v, w4.y, acc[q * 4 + 1]);
-                acc[q * 4 + 2] = fmaf(v, w4.z, acc[q * 4 + 2]);
-                acc[q * 4 + 3] = fmaf(v, w4.w, acc[q * 4 + 3]);
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float4* wr = reinterpret_cast<const float4*>(sw + ((dy * 3 + dx) * CIN + ci) * p.Cout + c0);
+                    float w[16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 w4 = wr[g];
+                        w[g * 4] = w4.x; w[g * 4 + 1] = w4.y; w[g * 4 + 2] = w4.z; w[g * 4 + 3] = w4.w;
+                    }
+#pragma unroll
+                    for (int q = 0; q < PX; ++q) {
+                        const float v = in[dy][q * STRIDE + dx][ci];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[q][j] = fmaf(v, w[j], acc[q][j]);
+                    }
+                }
+#pragma unroll
+        for (int q = 0; q < PX; ++q) {
+            if (obase[q] < 0) continue;
+            if (p.act == YRE_ACT_SILU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[q][j] = silu_f(acc[q][j]);
             }
+            st8<TOut>(p.y.ptr, obase[q] + c0, acc[q]);
+            st8<TOut>(p.y.ptr, obase[q] + c0 + 8, acc[q] + 8);
         }
-        if (p.act == YRE_ACT_SILU) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = silu_f(acc[j]);
-        }
-        st8<TOut>(p.y.ptr, obase + c0, acc);
-        st8<TOut>(p.y.ptr, obase + c0 + 8, acc + 8);
     }
 }
 
@@ -89,11 +112,11 @@ int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
     StemParams p;
     p.x = d.x_nchw; p.y = make_dview(d.y); p.w = d.w; p.bias = d.bias;
     p.B = d.B; p.Cin = d.Cin; p.H = d.H; p.W = d.W; p.Ho = Ho; p.Wo = Wo; p.Cout = d.y.C; p.stride = d.stride; p.act = d.act;
-    const long long total = (long long)d.B * Ho * Wo;
+    const long long total = (long long)d.B * Ho * ((Wo + PX - 1) / PX);
     const size_t smem = (size_t)(9 * d.Cin + 1) * d.y.C * sizeof(float);
     if (smem > 48 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "stem: Cout too large for the weight cache");
     dim3 grid(yre_cdiv(total, 128));
-#define STEM_GO(T, C) stem_kernel<T, C><<<grid, 128, smem, s>>>(p)
+#define STEM_GO(T, C) do { if (d.stride == 2) stem_kernel<T, C, 2><<<grid, 128, smem, s>>>(p); else stem_kernel<T, C, 1><<<grid, 128, smem, s>>>(p); } while (0)
 #define STEM_T(T) switch (d.Cin) { case 1: STEM_GO(T, 1); break; case 2: STEM_GO(T, 2); break; case 3: STEM_GO(T, 3); break; default: STEM_GO(T, 4); }
     if (d.y.dtype == YRE_F32) { STEM_T(float) } else { STEM_T(__nv_bfloat16) }
 #undef STEM_T

@@ -382,6 +382,24 @@ class Plan:
         self.lib.yre_plan_op_flops(self.h, fl, n)
         return [(self.lib.yre_plan_op_name(self.h, i).decode(), fl[i]) for i in range(n)]
 
+    def op_descriptions(self) -> list[str]:
+        """Human-readable shape of every recorded op (same order as op_table())."""
+        out = []
+        for kind, a in self.trace:
+            if kind == "conv":
+                x, y = a["x"], a["y"]
+                out.append(f"conv{a['k']}x{a['k']}s{a['stride']} {x.C}->{y.C} @{y.H}x{y.W} B{y.B}"
+                           f"{' +res' if a['res'] is not None else ''}{' f32out' if y.dtype == L.F32 else ''}")
+            elif kind == "stem":
+                y = a["y"]
+                out.append(f"stem {a['x'].shape[1]}->{y.C} @{y.H}x{y.W} B{y.B}")
+            elif kind in ("adown", "spp", "upsample"):
+                x = a["x"]
+                out.append(f"{kind} C{x.C} @{x.H}x{x.W} B{x.B}")
+            else:
+                out.append(kind)
+        return out
+
     def run_op(self, i: int) -> None:
         s = torch.cuda.current_stream(self.device).cuda_stream
         L.check(self.lib.yre_plan_run_op(self.h, i, s), "plan_run_op")
