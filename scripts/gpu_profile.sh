@@ -7,7 +7,7 @@ echo "== bench"; timeout 900 python bench.py --steps 20 --warmup 5 --per-op gpur
 if [ "$1" == "ncu" ]; then
   echo "== ncu launch list"
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
-  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 420 -c 300 --csv --log-file gpurun_out/launches.csv \
+  timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"conv_tc|conv_ffma|stem|adown|spp|upsample|decode|nms|cbfuse" -s 411 -c 274 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
   echo "== ncu conv_tc sections (one step, all 124 launches)"
   timeout 1500 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats --section Occupancy \

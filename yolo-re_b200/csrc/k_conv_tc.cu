@@ -17,10 +17,15 @@
 // epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Warp roles (256 threads, 1 CTA / SM, persistent over a static tile schedule):
-//   warp 0 lane 0 : TMA producer          warp 1 lane 0 : tcgen05.mma issuer
-//   warp 2        : TMEM alloc / dealloc  warps 4..7     : epilogue (TMEM lane quarter = warp % 4)
-// Epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16/fp32 -> global, written into the
-// consumer's channel window (concat-slice write).
+//   warp 0 : TMA producer          warp 1 : tcgen05.mma issuer       warp 2 : TMEM alloc / dealloc
+//   warps 4..11 : epilogue; warp w owns TMEM lane quarter w%4 (32 pixels) and every other 32-column
+//   chunk, with its own double-buffered staging tile and its own TMA stores -- no CTA-wide barrier
+// Epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> 128B-swizzled shared-memory staging
+// tile -> TMA store (cp.async.bulk.tensor) into the consumer's channel window (concat-slice write,
+// ragged tile edges clipped by the TMA unit).  fp32 outputs (the raw head logits) use direct 16-byte
+// stores.  All role loops are warp-uniform (elect.sync picks the issuing lane), which keeps the
+// descriptors in uniform registers -- a lane-0 branch made ptxas wrap every UTCHMMA/UTMALDG in a
+// serialising ELECT loop (profiles/r01_notes.md).
 #include "yre_common.cuh"
 #include <cuda.h>
 #include <cstring>
@@ -30,7 +35,7 @@ struct ConvTcPlan;
 
 namespace {
 
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;    // 12 warps: TMA, MMA, TMEM-alloc, spare, 8 epilogue
 constexpr int BLOCK_M = 128;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_STRIDE = 256;     // columns between the two accumulator buffers
@@ -51,6 +56,9 @@ struct TcParams {
     void* y; int y_f32; int y_ctot, y_coff;
     const void* res; int res_f32; int res_ctot, res_coff;
     int* dbg;                       // optional watchdog record (may be null)
+    int tma_store;                  // 1: bf16 output through the smem-staged TMA store
+    int stw, sth, stb;              // the 32 pixels of one TMEM lane quarter as a (stb x sth x stw) sub-patch
+    uint32_t stage_out_bytes;       // bytes of one per-warp staging buffer (32 rows x 32 ch x 2 = 2048)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -112,6 +120,21 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\t@px mov.s32 %0, 1;\n\t}"
+                 : "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred;
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -152,6 +175,16 @@ __device__ __forceinline__ float silu_fast(float x) {
     return fmaf(h, t, h);
 }
 
+// optional timeline trace (YRE_TC_TRACE=1): CTA 0 records (role, event, clock) triples
+__device__ __forceinline__ void trace(int* dbg, int role, int& n, int ev) {
+    if (dbg && blockIdx.x == 0 && n < 96) {
+        long long c = clock64();
+        int* slot = dbg + 16 + ((role * 96 + n) * 4);
+        slot[0] = ev; slot[1] = (int)(c & 0xffffffffll); slot[2] = (int)(c >> 32); slot[3] = 1;
+        ++n;
+    }
+}
+
 // K-major shared-memory matrix descriptor (sm_100 "version 1"), start address advanced by the caller
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo16, uint32_t layout_type) {
     uint64_t d = 0;
@@ -163,10 +196,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
     return d;
 }
 
-// epilogue for NC columns held in v[] (fp32 bit patterns), columns [c0, c0+NC) of the CTA tile
+// epilogue math for NC accumulator columns [n, n+NC): +bias -> SiLU -> (+residual), result in f[]
 template <int NC>
-__device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t* v, bool valid, long long pix, int n) {
-    float f[NC];
+__device__ __forceinline__ void epilogue_math(const TcParams& p, const uint32_t* v, float* f, bool valid, long long pix, int n) {
 #pragma unroll
     for (int i = 0; i < NC; ++i) f[i] = __uint_as_float(v[i]);
     if (p.bias) {
@@ -180,8 +212,7 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
 #pragma unroll
         for (int i = 0; i < NC; ++i) f[i] = silu_fast(f[i]);
     }
-    if (!valid) return;
-    if (p.res) {
+    if (p.res && valid) {
         if (p.res_f32) {
             const float* r = reinterpret_cast<const float*>(p.res) + pix * p.res_ctot + p.res_coff + n;
 #pragma unroll
@@ -201,6 +232,11 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
             }
         }
     }
+}
+
+// direct global store of NC columns (fp32 or bf16 output)
+template <int NC>
+__device__ __forceinline__ void store_direct(const TcParams& p, const float* f, long long pix, int n) {
     if (p.y_f32) {
         float* o = reinterpret_cast<float*>(p.y) + pix * p.y_ctot + p.y_coff + n;
 #pragma unroll
@@ -217,24 +253,38 @@ __device__ __forceinline__ void epilogue_store(const TcParams& p, const uint32_t
     }
 }
 
+// 32 bf16 columns of one row into the swizzled staging tile.  `row_base` = smem address of the row,
+// `c16` = first 16-byte chunk inside the row, `sw` = XOR pattern of the row (matches the TMA swizzle).
+__device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base, uint32_t c16, uint32_t sw) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = row_base + (((c16 + q) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                     "r"(pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1])), "r"(pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3])),
+                     "r"(pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5])), "r"(pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7])) : "memory");
+    }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    const uint32_t bar_base = sbase + (uint32_t)p.stages * stage_bytes;
-    // barrier i at bar_base + 8*i : full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4)
     const uint32_t S = (uint32_t)p.stages;
+    const uint32_t out_base = sbase + S * stage_bytes;       // 8 warps x 2 staging buffers for the TMA-store epilogue
+    const uint32_t bar_base = out_base + 16u * p.stage_out_bytes;
+    // barrier i at bar_base + 8*i : full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4)
     const uint32_t tmem_slot = bar_base + 8u * (2u * S + 4u);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); if (p.tma_store) tma_prefetch_desc(&tmY); }
     if (warp == 1 && lane == 0) {
         for (uint32_t i = 0; i < S; ++i) { mbar_init(bar_base + 8u * i, 1); mbar_init(bar_base + 8u * (S + i), 1); }
-        for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_base + 8u * (2u * S + i), 1); mbar_init(bar_base + 8u * (2u * S + 2u + i), 4); }
+        for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_base + 8u * (2u * S + i), 1); mbar_init(bar_base + 8u * (2u * S + 2u + i), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -248,102 +298,160 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int kiters = p.taps * p.kchunks;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            // ================= TMA producer =================
-            uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                const int nt = t % p.tiles_n; int mt = t / p.tiles_n;
-                const int xt = mt % p.tiles_x; mt /= p.tiles_x;
-                const int yt = mt % p.tiles_y; const int bt = mt / p.tiles_y;
-                const int x0 = xt * p.tw, y0 = yt * p.th, b0 = bt * p.tb, n0 = nt * p.block_n;
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    int dx = 0, dy = 0, plane = 0;
-                    if (p.taps == 9) {
-                        const int ky = tap / 3, kx = tap % 3;
-                        if (p.phase4) {   // input row 2*oy + ky - 1  ->  parity (ky != 1), plane row oy - (ky == 0)
-                            plane = ((ky != 1) << 1) | (kx != 1);
-                            dy = (ky == 0) ? -1 : 0; dx = (kx == 0) ? -1 : 0;
-                        } else { dy = ky - 1; dx = kx - 1; }
-                    }
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (S + stage);
-                        mbar_wait(empty, phase ^ 1u, p.dbg, 1);
+    // Two independent (producer, MMA-issuer) warp pairs ping-pong over the CTA's tiles: pair `pipe` takes the
+    // local tiles j with (j & 1) == pipe, owns half of the shared-memory stage ring and accumulator buffer
+    // `pipe`.  One issuing thread needs ~600 cycles per k-iteration (mbarrier wait + descriptor math on the
+    // uniform datapath + commit); two of them keep the tensor pipe and the TMA unit fed.
+    const uint32_t S2 = S >> 1;
+    if (warp == 0 || warp == 2) {
+        // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
+        const uint32_t pipe = (uint32_t)warp >> 1;
+        uint32_t stage = 0, phase = 0;
+        int tn = 0;
+        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += 2 * gridDim.x) {
+            const int nt = t % p.tiles_n; int mt = t / p.tiles_n;
+            const int xt = mt % p.tiles_x; mt /= p.tiles_x;
+            const int yt = mt % p.tiles_y; const int bt = mt / p.tiles_y;
+            const int x0 = xt * p.tw, y0 = yt * p.th, b0 = bt * p.tb, n0 = nt * p.block_n;
+            for (int tap = 0; tap < p.taps; ++tap) {
+                int dx = 0, dy = 0, plane = 0;
+                if (p.taps == 9) {
+                    const int ky = tap / 3, kx = tap - 3 * ky;
+                    if (p.phase4) {   // input row 2*oy + ky - 1  ->  parity (ky != 1), plane row oy - (ky == 0)
+                        plane = ((ky != 1) << 1) | (kx != 1);
+                        dy = (ky == 0) ? -1 : 0; dx = (kx == 0) ? -1 : 0;
+                    } else { dy = ky - 1; dx = kx - 1; }
+                }
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    const uint32_t gs = pipe * S2 + stage;
+                    const uint32_t full = bar_base + 8u * gs, empty = bar_base + 8u * (S + gs);
+                    mbar_wait(empty, phase ^ 1u, p.dbg, 1);
+                    if (pipe == 0 && lane == 0) trace(p.dbg, 0, tn, 1);
+                    if (elect_one()) {
                         mbar_expect_tx(full, stage_bytes);
-                        const uint32_t sa = sbase + stage * stage_bytes, sb = sa + p.a_bytes;
+                        const uint32_t sa = sbase + gs * stage_bytes, sb = sa + p.a_bytes;
                         const int c = p.x_coff + kc * p.block_k;
                         if (p.phase4) tma_load_5d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
                         else tma_load_4d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0);
                         tma_load_2d(sb, &tmB, full, tap * p.Cin + kc * p.block_k, n0);
-                        if (++stage == S) { stage = 0; phase ^= 1u; }
                     }
+                    __syncwarp();
+                    if (pipe == 0 && lane == 0) trace(p.dbg, 0, tn, 2);
+                    if (++stage == S2) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ================= MMA issuer =================
-            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            const int ksteps = p.block_k / 16;
-            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-                const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 2u + acc);
-                mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
+    } else if (warp == 1 || warp == 3) {
+        // ================= MMA issuer (warp-uniform loop, elected lane issues) =================
+        const uint32_t pipe = (uint32_t)warp >> 1;
+        uint32_t stage = 0, phase = 0, acc_phase = 0;
+        const int ksteps = p.block_k >> 4;
+        const uint64_t desc0 = make_smem_desc(0, p.sbo16, p.layout_type);
+        const uint32_t tfull = bar_base + 8u * (2u * S + pipe), tempty = bar_base + 8u * (2u * S + 2u + pipe);
+        const uint32_t d_tmem = tmem_base + pipe * ACC_STRIDE;
+        int tn = 0;
+        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += 2 * gridDim.x) {
+            mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
+            tc_fence_after();
+            if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 10);
+            for (int it = 0; it < kiters; ++it) {
+                const uint32_t gs = pipe * S2 + stage;
+                const uint32_t full = bar_base + 8u * gs, empty = bar_base + 8u * (S + gs);
+                mbar_wait(full, phase, p.dbg, 3);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
-                for (int it = 0; it < kiters; ++it) {
-                    const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (S + stage);
-                    mbar_wait(full, phase, p.dbg, 3);
-                    tc_fence_after();
-                    const uint32_t sa = sbase + stage * stage_bytes, sb = sa + p.a_bytes;
-                    const uint64_t da = make_smem_desc(sa, p.sbo16, p.layout_type);
-                    const uint64_t db = make_smem_desc(sb, p.sbo16, p.layout_type);
-                    for (int k = 0; k < ksteps; ++k) {
-                        // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in the >>4 address field
+                if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 11);
+                if (elect_one()) {
+                    const uint32_t sa = sbase + gs * stage_bytes, sb = sa + p.a_bytes;
+                    const uint64_t da = desc0 | (uint64_t)((sa >> 4) & 0x3FFFu);
+                    const uint64_t db = desc0 | (uint64_t)((sb >> 4) & 0x3FFFu);
+                    for (int k = 0; k < ksteps; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the >>4 address field
                         umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (it | k) ? 1u : 0u);
-                    }
                     umma_commit(empty);                       // frees the smem stage when these MMAs retire
                     if (it == kiters - 1) umma_commit(tfull); // accumulator complete -> epilogue
-                    if (++stage == S) { stage = 0; phase ^= 1u; }
                 }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                __syncwarp();
+                if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 12);
+                if (++stage == S2) { stage = 0; phase ^= 1u; }
             }
+            acc_phase ^= 1u;
         }
     } else if (warp >= 4) {
-        // ================= epilogue =================
-        const int ew = warp & 3;
-        const int row = ew * 32 + lane;
+        // ================= epilogue (8 warps, warp-local: no CTA barrier) =================
+        const int q = warp & 3;                 // TMEM lane quarter -> rows 32q .. 32q+31 of the tile
+        const int hsel = (warp - 4) >> 2;       // takes the 32-column chunks c with (c & 1) == hsel
+        const int row = q * 32 + lane;
         const int patch = p.tw * p.th;
         const int bi = row / patch, rem = row % patch, yy = rem / p.tw, xx = rem % p.tw;
-        uint32_t acc = 0, acc_phase = 0;
+        // origin of this warp's 32-pixel sub-patch inside the tile (row 32q)
+        const int r0 = q * 32, sb0 = r0 / patch, sy0 = (r0 % patch) / p.tw, sx0 = (r0 % patch) % p.tw;
+        const uint32_t stg = out_base + (uint32_t)(warp - 4) * 2u * p.stage_out_bytes;
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);         // SWIZZLE_64B pattern of this row
+        const int nchunks = (p.block_n + 31) >> 5;
+        uint32_t acc = 0, acc_phase = 0, obuf = 0;
+        int tn = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             const int nt = t % p.tiles_n; int mt = t / p.tiles_n;
             const int xt = mt % p.tiles_x; mt /= p.tiles_x;
             const int yt = mt % p.tiles_y; const int bt = mt / p.tiles_y;
-            const int x = xt * p.tw + xx, y = yt * p.th + yy, b = bt * p.tb + bi, n0 = nt * p.block_n;
+            const int x0 = xt * p.tw, y0 = yt * p.th, b0 = bt * p.tb, n0 = nt * p.block_n;
+            const int x = x0 + xx, y = y0 + yy, b = b0 + bi;
             const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
             const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
             const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 2u + acc);
+            if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 20);
             mbar_wait(tfull, acc_phase, p.dbg, 4);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * ACC_STRIDE;
-            int c = 0;
-            for (; c + 32 <= p.block_n; c += 32) {
-                uint32_t v[32];
-                TMEM_LD32(taddr + (uint32_t)c, v);
-                tmem_ld_wait();
-                epilogue_store<32>(p, v, valid, pix, n0 + c);
+            if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 21);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
+            uint32_t v[32];
+            int c = hsel;
+            bool have = false;
+            if (c < nchunks && c * 32 + 32 <= p.block_n) { TMEM_LD32(taddr + (uint32_t)(c * 32), v); have = true; }
+            for (; c < nchunks; c += 2) {
+                const int col = c * 32;
+                if (have) {
+                    uint32_t w[32];
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) w[i] = v[i];
+                    // prefetch this warp's next chunk while the current one is processed
+                    const int cn = c + 2;
+                    have = (cn < nchunks && cn * 32 + 32 <= p.block_n);
+                    if (have) TMEM_LD32(taddr + (uint32_t)(cn * 32), v);
+                    float f[32];
+                    epilogue_math<32>(p, w, f, valid, pix, n0 + col);
+                    if (p.tma_store) {
+                        if (lane == 0) bulk_wait_read<1>();      // the store that used this buffer two chunks ago has read it
+                        __syncwarp();
+                        const uint32_t buf = stg + obuf * p.stage_out_bytes;
+                        store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&tmY, buf, p.y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
+                            bulk_commit();
+                        }
+                        obuf ^= 1u;
+                    } else if (valid) {
+                        store_direct<32>(p, f, pix, n0 + col);
+                    }
+                } else {                         // 16-column tail (block_n % 32 == 16, direct-store outputs only)
+                    uint32_t w16[16];
+                    float f[16];
+                    TMEM_LD16(taddr + (uint32_t)col, w16);
+                    tmem_ld_wait();
+                    epilogue_math<16>(p, w16, f, valid, pix, n0 + col);
+                    if (valid) store_direct<16>(p, f, pix, n0 + col);
+                }
             }
-            if (c < p.block_n) {   // block_n % 32 == 16
-                uint32_t v[16];
-                TMEM_LD16(taddr + (uint32_t)c, v);
-                tmem_ld_wait();
-                epilogue_store<16>(p, v, valid, pix, n0 + c);
-            }
+            // every tcgen05.ld of this accumulator has completed: hand the TMEM buffer back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty);
+            if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 22);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (p.tma_store && lane == 0) bulk_wait_all();           // stores must land before the CTA retires
     }
 
     tc_fence_before();
@@ -373,6 +481,8 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
+int* g_trace_buf = nullptr;
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -381,7 +491,7 @@ int env_int(const char* name, int dflt) {
 }  // namespace
 
 struct ConvTcPlan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmY;
     TcParams p;
     int grid;
     size_t smem;
@@ -403,6 +513,7 @@ int conv_tc_eligible(const yre_conv_desc& d, char* why, size_t n) {
         if (d.res.layout != YRE_NHWC || d.res.c_off % ral || d.res.C_total % ral) NOPE("residual must be an aligned NHWC window");
     }
     if ((reinterpret_cast<uintptr_t>(d.x.ptr) & 127) || (reinterpret_cast<uintptr_t>(d.w) & 127)) NOPE("x and w must be 128-byte aligned");
+    if (reinterpret_cast<uintptr_t>(d.y.ptr) & 127) NOPE("y must be 128-byte aligned");
     if (d.bias && (reinterpret_cast<uintptr_t>(d.bias) & 15)) NOPE("bias must be 16-byte aligned");
     if (!get_encode()) NOPE("cuTensorMapEncodeTiled unavailable");
     return 1;
@@ -452,19 +563,34 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     p.a_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
     p.b_bytes = (uint32_t)(bn * p.block_k * 2);
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    int stages = (int)((200u * 1024u) / stage_bytes);
+    // bf16 outputs leave through a swizzled staging tile + TMA store; fp32 outputs (raw head logits) store directly
+    p.tma_store = (d.y.dtype == YRE_BF16 && bn % 32 == 0 && env_int("YRE_TC_DIRECT_STORE", 0) == 0) ? 1 : 0;
+    p.stage_out_bytes = p.tma_store ? 2048u : 0u;                    // 32 rows x 32 channels x bf16 per buffer
+    p.stw = p.tw < 32 ? p.tw : 32;
+    p.sth = (32 / p.stw) < p.th ? (32 / p.stw) : p.th;
+    p.stb = 32 / (p.stw * p.sth);
+    const uint32_t smem_cap = 227u * 1024u - 1024u - 256u;          // alignment slack + barriers
+    int stages = (int)((smem_cap - 16u * p.stage_out_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
     const int force_st = env_int("YRE_TC_STAGES", 0);
-    if (force_st >= 2 && force_st <= stages) stages = force_st;
-    if (stages < 2) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: tile does not fit shared memory"); }
+    if (force_st >= 4 && force_st <= stages) stages = force_st;
+    stages &= ~1;                                                    // two pipelines share the ring
+    if (stages < 4) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: tile does not fit shared memory"); }
     p.stages = stages;
-    pl->smem = (size_t)stages * stage_bytes + 8 * (2 * stages + 4) + 16 + 1024;
+    pl->smem = (size_t)stages * stage_bytes + 16 * p.stage_out_bytes + 8 * (2 * stages + 4) + 16 + 1024;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     p.bias = d.bias; p.act = d.act;
     p.y = d.y.ptr; p.y_f32 = d.y.dtype == YRE_F32; p.y_ctot = d.y.C_total; p.y_coff = d.y.c_off;
     p.res = d.res.ptr; p.res_f32 = d.res.ptr ? d.res.dtype == YRE_F32 : 0;
     p.res_ctot = d.res.ptr ? d.res.C_total : 0; p.res_coff = d.res.ptr ? d.res.c_off : 0;
     p.dbg = nullptr;
+    if (env_int("YRE_TC_TRACE", 0)) {
+        static int* g_dbg = nullptr;
+        if (!g_dbg) { cudaMalloc(&g_dbg, 8192 * sizeof(int)); }
+        cudaMemset(g_dbg, 0, 8192 * sizeof(int));
+        p.dbg = g_dbg;
+        g_trace_buf = g_dbg;
+    }
     pl->grid = p.num_tiles < sms ? p.num_tiles : sms;
 
     // ---- tensor maps ----
@@ -497,6 +623,17 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r); }
+    if (p.tma_store) {
+        cuuint64_t gdim[4] = {(cuuint64_t)d.y.C_total, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)d.y.C_total * 2, (cuuint64_t)Wo * d.y.C_total * 2, (cuuint64_t)Ho * Wo * d.y.C_total * 2};
+        cuuint32_t box[4] = {32u, (cuuint32_t)p.stw, (cuuint32_t)p.sth, (cuuint32_t)p.stb};
+        cuuint32_t est[4] = {1, 1, 1, 1};
+        r = enc(&pl->tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.y.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(Y) failed with %d", (int)r); }
+    } else {
+        pl->tmY = pl->tmB;   // unused
+    }
     *out = pl;
     return YRE_OK;
 }
@@ -507,7 +644,7 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
         YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    conv_tc_kernel<<<pl->grid, NUM_THREADS, pl->smem, s>>>(pl->tmA, pl->tmB, pl->p);
+    conv_tc_kernel<<<pl->grid, NUM_THREADS, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
     YRE_LAUNCH_CHECK("conv_tc");
     return YRE_OK;
 }
@@ -516,7 +653,18 @@ void conv_tc_free(ConvTcPlan* p) { delete p; }
 
 int conv_tc_rebind(ConvTcPlan* pl, const void* old_ptr, void* new_ptr) {
     int n = 0;
-    if (pl->p.y == old_ptr) { pl->p.y = new_ptr; ++n; }
+    if (pl->p.y == old_ptr) {
+        if (pl->p.tma_store) return -1;          // output is baked into a TMA tensor map
+        pl->p.y = new_ptr; ++n;
+    }
     if (pl->p.res == old_ptr) { pl->p.res = new_ptr; ++n; }
     return n;
+}
+
+// debugging aid: copies the last trace buffer (8192 ints) to the host; returns 0 when tracing is off
+extern "C" int yre_debug_read_trace(int* host, int n) {
+    if (!g_trace_buf) return 0;
+    cudaDeviceSynchronize();
+    cudaMemcpy(host, g_trace_buf, sizeof(int) * (n < 8192 ? n : 8192), cudaMemcpyDeviceToHost);
+    return n < 8192 ? n : 8192;
 }

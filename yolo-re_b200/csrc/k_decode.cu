@@ -42,17 +42,26 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams p) {
     const int na = min(TILE, p.A - a0);
     const int tid = threadIdx.x;
 
-    // ---- stage raw rows (coalesced 4-channel chunks) ----
-    const int chunks = CH / 4;
-    for (int i = tid; i < na * chunks; i += blockDim.x) {
-        const int al = i / chunks, ck = i % chunks;
-        const int a = a0 + al;
+    // ---- per-anchor source offset (level lookup + div/mod once per anchor, not once per load) ----
+    __shared__ long long s_src[TILE];
+    __shared__ float s_ax[TILE], s_ay[TILE], s_st[TILE];
+    if (tid < na) {
+        const int a = a0 + tid;
         int l = 0;
         while (l + 1 < p.levels && a >= p.a_start[l + 1]) ++l;
         const int r = a - p.a_start[l];
         const DView& v = p.raw[l];
-        const int py = r / v.W, px = r % v.W;
-        const float4 q = ld4<T>(v.ptr, dview_pix(v, b, py, px) + ck * 4);
+        const int py = r / v.W, px = r - py * v.W;
+        s_src[tid] = dview_pix(v, b, py, px) | ((long long)l << 56);
+        s_ax[tid] = (float)px + 0.5f; s_ay[tid] = (float)py + 0.5f; s_st[tid] = p.stride[l];
+    }
+    __syncthreads();
+    // ---- stage raw rows (coalesced 4-channel chunks) ----
+    const int chunks = CH / 4;
+    for (int i = tid; i < na * chunks; i += blockDim.x) {
+        const int al = i / chunks, ck = i - al * chunks;
+        const long long src = s_src[al];
+        const float4 q = ld4<T>(p.raw[(int)(src >> 56)].ptr, (src & 0x00ffffffffffffffll) + ck * 4);
         *reinterpret_cast<float4*>(s_raw + al * PITCH + ck * 4) = q;
     }
     __syncthreads();
@@ -85,12 +94,7 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams p) {
 
     // ---- boxes: thread = anchor ----
     if (tid < na) {
-        const int a = a0 + tid;
-        int l = 0;
-        while (l + 1 < p.levels && a >= p.a_start[l + 1]) ++l;
-        const int r = a - p.a_start[l];
-        const int W = p.raw[l].W;
-        const float ax = (float)(r % W) + 0.5f, ay = (float)(r / W) + 0.5f, st = p.stride[l];
+        const float ax = s_ax[tid], ay = s_ay[tid], st = s_st[tid];
         const float x1 = ax - s_e[tid * 4 + 0], y1 = ay - s_e[tid * 4 + 1];
         const float x2 = ax + s_e[tid * 4 + 2], y2 = ay + s_e[tid * 4 + 3];
         float* o = s_out + tid * OC;

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(128) nms_filter_kernel(const FilterParams p) {
     const int na = min(32, p.A - a0);
     const float4* base = reinterpret_cast<const float4*>(p.pred + ((size_t)b * p.A + a0) * (4 + p.nc));
 
-    for (int idx = lane; idx < na * n4; idx += 32) {
+    const bool vec = (p.nc & 3) == 0;        // rows are 16-byte aligned only when nc % 4 == 0
+    for (int idx = lane; vec && idx < na * n4; idx += 32) {
         const int al = idx / n4, pos = idx % n4;
         if (pos == 0) continue;
         const float4 v = base[idx];
@@ -92,10 +93,19 @@ __global__ void __launch_bounds__(128) nms_filter_kernel(const FilterParams p) {
     float conf = 0.f; int cls = 0;
     float x1 = 0, y1 = 0, x2 = 0, y2 = 0;
     if (lane < na) {
-        conf = pv[lane * pitch]; cls = pi[lane * pitch];
-        for (int q = 1; q < nparts; ++q) {
-            const float v = pv[lane * pitch + q];
-            if (v > conf) { conf = v; cls = pi[lane * pitch + q]; }     // strict > keeps the first max
+        if (vec) {
+            conf = pv[lane * pitch]; cls = pi[lane * pitch];
+            for (int q = 1; q < nparts; ++q) {
+                const float v = pv[lane * pitch + q];
+                if (v > conf) { conf = v; cls = pi[lane * pitch + q]; }     // strict > keeps the first max
+            }
+        } else {                              // generic class count: one lane walks its own row
+            const float* row = p.pred + ((size_t)b * p.A + a0 + lane) * (4 + p.nc);
+            conf = row[4];
+            for (int q = 1; q < p.nc; ++q) {
+                const float v = row[4 + q];
+                if (v > conf) { conf = v; cls = q; }
+            }
         }
         cand = conf > p.conf;
         if (cand && p.n_classes >= 0) {
@@ -104,7 +114,8 @@ __global__ void __launch_bounds__(128) nms_filter_kernel(const FilterParams p) {
             cand = ok;
         }
         if (cand) {
-            const float4 bx = base[lane * n4];
+            const float* brow = p.pred + ((size_t)b * p.A + a0 + lane) * (4 + p.nc);
+            const float4 bx = vec ? base[lane * n4] : make_float4(brow[0], brow[1], brow[2], brow[3]);
             const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);   // w/2, h/2 (exact)
             x1 = __fsub_rn(bx.x, hw); y1 = __fsub_rn(bx.y, hh);
             x2 = __fadd_rn(bx.x, hw); y2 = __fadd_rn(bx.y, hh);
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
             const float conf = ord2f(~(unsigned)(key >> 32));
             const int cls = p.ws.cls[(size_t)b * p.A + a];
             const float* row = p.pred + ((size_t)b * p.A + a) * rowf;
-            const float4 bx = *reinterpret_cast<const float4*>(row);
+            const float4 bx = (p.nc & 3) ? make_float4(row[0], row[1], row[2], row[3]) : *reinterpret_cast<const float4*>(row);
             const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);
             float4 u;
             u.x = __fsub_rn(bx.x, hw); u.y = __fsub_rn(bx.y, hh); u.z = __fadd_rn(bx.x, hw); u.w = __fadd_rn(bx.y, hh);
@@ -313,7 +324,6 @@ extern "C" size_t yre_nms_workspace_bytes(int32_t B, int32_t A) {
 int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
     if (!d.pred || !d.out || !d.counts || !d.keep_anchor || !d.workspace) YRE_FAIL(YRE_EINVAL, "nms: null pointer");
     if (d.B <= 0 || d.A <= 0 || d.nc <= 0) YRE_FAIL(YRE_EINVAL, "nms: bad extent B=%d A=%d nc=%d", d.B, d.A, d.nc);
-    if (d.nc % 4) YRE_FAIL(YRE_EUNSUPPORTED, "nms: nc=%d must be a multiple of 4", d.nc);
     if (d.max_det <= 0 || d.max_det > 4096) YRE_FAIL(YRE_EUNSUPPORTED, "nms: max_det=%d (supported 1..4096)", d.max_det);
     if (d.workspace_bytes < yre_nms_workspace_bytes(d.B, d.A)) YRE_FAIL(YRE_EINVAL, "nms: workspace too small");
     if (d.n_classes > 0 && !d.classes) YRE_FAIL(YRE_EINVAL, "nms: classes pointer missing");
@@ -327,7 +337,7 @@ int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
     FilterParams fp;
     fp.pred = d.pred; fp.B = d.B; fp.A = d.A; fp.nc = d.nc; fp.conf = d.conf_thres;
     fp.classes = d.classes; fp.n_classes = d.n_classes; fp.ws = ws;
-    const size_t per_warp = (size_t)32 * ((d.nc / 4) | 1) * 8;
+    const size_t per_warp = (d.nc % 4 == 0) ? (size_t)32 * ((d.nc / 4) | 1) * 8 : 16;
     int warps = 4;
     while (warps > 1 && per_warp * warps > 40 * 1024) warps >>= 1;
     if (per_warp * warps > 48 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "nms: nc=%d too large", d.nc);

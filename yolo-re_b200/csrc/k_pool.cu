@@ -109,6 +109,124 @@ __global__ void __launch_bounds__(256, 2) adown_prepool_kernel(DView x, DView lo
     }
 }
 
+// K3, tiled variant: a CTA stages a (2*TY+2) x (2*TX+2) input patch of 128 BYTES per pixel (64 bf16 /
+// 32 fp32 channels = whole 128-byte lines, so HBM is read once) in shared memory in its storage type,
+// then emits TY x TX cells of the stride-2 grid from it.  Pixel pitch 144 B: consecutive pixels start
+// 4 banks apart, which makes the 16-byte shared-memory accesses conflict-free.
+constexpr int AD_TY = 4, AD_TX = 16;
+constexpr int AD_ROWS = 2 * AD_TY + 2, AD_COLS = 2 * AD_TX + 2;
+
+template <typename T> struct SmemPix;
+template <> struct SmemPix<__nv_bfloat16> {
+    static constexpr int CHN = 64;
+    static __device__ __forceinline__ void ld(const uint4* px, int g, float* o) {      // 8 channels of group g
+        const uint4 u = px[g];
+        o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+        o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+        o[4] = __uint_as_float(u.z << 16); o[5] = __uint_as_float(u.z & 0xffff0000u);
+        o[6] = __uint_as_float(u.w << 16); o[7] = __uint_as_float(u.w & 0xffff0000u);
+    }
+};
+template <> struct SmemPix<float> {
+    static constexpr int CHN = 32;
+    static __device__ __forceinline__ void ld(const uint4* px, int g, float* o) {
+        const uint4 a = px[2 * g], b = px[2 * g + 1];
+        o[0] = __uint_as_float(a.x); o[1] = __uint_as_float(a.y); o[2] = __uint_as_float(a.z); o[3] = __uint_as_float(a.w);
+        o[4] = __uint_as_float(b.x); o[5] = __uint_as_float(b.y); o[6] = __uint_as_float(b.z); o[7] = __uint_as_float(b.w);
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3) adown_tiled_kernel(DView x, DView lo, DView hi, int half, int tiles_x, int tiles_y) {
+    constexpr int CHN = SmemPix<T>::CHN, G = CHN / 8;
+    __shared__ uint4 tile[AD_ROWS][AD_COLS][9];        // 8 x 16 B of data + 16 B pad per pixel
+    int t = blockIdx.x;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int c0 = blockIdx.y * CHN;                   // channel chunk: entirely in the low or the high half
+    const int oy0 = ty * AD_TY, ox0 = tx * AD_TX;
+    const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+    const int Ha = x.H - 1, Wa = x.W - 1;
+    const int tid = threadIdx.x;
+    const T* xp = reinterpret_cast<const T*>(x.ptr);
+
+    for (int i = tid; i < AD_ROWS * AD_COLS * 8; i += 256) {
+        const int v = i & 7, pix = i >> 3;
+        const int r = pix / AD_COLS, c = pix - r * AD_COLS;
+        const int iy = iy0 + r, ix = ix0 + c;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (iy >= 0 && iy < x.H && ix >= 0 && ix < x.W)
+            u = *reinterpret_cast<const uint4*>(xp + dview_pix(x, b, iy, ix) + c0 + v * (16 / (int)sizeof(T)));
+        tile[r][c][v] = u;
+    }
+    __syncthreads();
+
+    if (c0 < half) {
+        // (2*TY) x (2*TX) average pixels x G channel groups; item -> (ayl, axl, g), g fastest
+        for (int i = tid; i < 2 * AD_TY * 2 * AD_TX * G; i += 256) {
+            const int g = i % G;
+            const int axl = (i / G) % (2 * AD_TX), ayl = i / (G * 2 * AD_TX);
+            const int ay = 2 * oy0 + ayl, ax = 2 * ox0 + axl;
+            const bool ok = ay < Ha && ax < Wa;
+            float o[8];
+            if (ok) {
+                float a[8], bq[8], cq[8], d[8];
+                SmemPix<T>::ld(tile[ayl + 1][axl + 1], g, a);
+                SmemPix<T>::ld(tile[ayl + 1][axl + 2], g, bq);
+                SmemPix<T>::ld(tile[ayl + 2][axl + 1], g, cq);
+                SmemPix<T>::ld(tile[ayl + 2][axl + 2], g, d);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = (((a[e] + bq[e]) + cq[e]) + d[e]) * 0.25f;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = 0.f;
+            }
+            if (lo.layout == YRE_PHASE4) {
+                if ((ay >> 1) < lo.Hp && (ax >> 1) < lo.Wp) st8<T>(lo.ptr, dview_pix(lo, b, ay, ax) + c0 + g * 8, o);
+            } else if (ok) {
+                st8<T>(lo.ptr, dview_pix(lo, b, ay, ax) + c0 + g * 8, o);
+            }
+        }
+    } else {
+        // TY x TX cells x G groups: the 4x4 input window is read once, rows stream through registers
+        for (int i = tid; i < AD_TY * AD_TX * G; i += 256) {
+            const int g = i % G;
+            const int oxl = (i / G) % AD_TX, oyl = i / (G * AD_TX);
+            const int oy = oy0 + oyl, ox = ox0 + oxl;
+            if (oy >= hi.H || ox >= hi.W) continue;
+            float m[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m[e] = -FLT_MAX;
+            float prev[4][8], cur[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) SmemPix<T>::ld(tile[2 * oyl][2 * oxl + q], g, prev[q]);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {                 // average row ay = 2*oy - 1 + j uses tile rows 2*oyl+j, +1
+#pragma unroll
+                for (int q = 0; q < 4; ++q) SmemPix<T>::ld(tile[2 * oyl + j + 1][2 * oxl + q], g, cur[q]);
+                const int ay = 2 * oy - 1 + j;
+                if (ay >= 0 && ay < Ha) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const int ax = 2 * ox - 1 + q;
+                        if (ax >= 0 && ax < Wa) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                m[e] = fmaxf(m[e], (((prev[q][e] + prev[q + 1][e]) + cur[q][e]) + cur[q + 1][e]) * 0.25f);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) prev[q][e] = cur[q][e];
+            }
+            st8<T>(hi.ptr, dview_pix(hi, b, oy, ox) + (c0 - half) + g * 8, m);
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // K4: windows 5/9/13 max (== three chained MaxPool2d(5,1,2); reference sppelan.py:44-47)
 template <typename T>
@@ -147,6 +265,67 @@ __global__ void __launch_bounds__(256) spp_kernel(DView x, DView y5, DView y9, D
     st8<T>(y5.ptr, dview_pix(y5, b, py, px) + c, m5);
     st8<T>(y9.ptr, dview_pix(y9, b, py, px) + c, m9);
     st8<T>(y13.ptr, dview_pix(y13, b, py, px) + c, m13);
+}
+
+// K4, plane-resident variant: one CTA keeps a whole HxW plane of CHK channels in shared memory and runs
+// the reference's three chained 5x5 pools literally (each as a row pass + a column pass, ping-ponging
+// between two buffers): 30 shared-memory reads per element instead of 169 global loads.  max() is exact,
+// so the result is bit-identical to the direct kernel.
+template <typename T>
+__global__ void __launch_bounds__(256) spp_plane_kernel(DView x, DView y5, DView y9, DView y13, int chk) {
+    extern __shared__ __align__(16) float sp[];
+    const int H = x.H, W = x.W, g4 = chk / 4;
+    const int plane = H * W * chk;
+    float* A = sp;
+    float* Bf = sp + plane;
+    const int b = blockIdx.x, c0 = blockIdx.y * chk;
+    const int items8 = H * W * (chk / 8);
+    for (int i = threadIdx.x; i < items8; i += blockDim.x) {
+        const int g = i % (chk / 8), pix = i / (chk / 8);
+        float f[8];
+        ld8<T>(x.ptr, dview_pix(x, b, pix / W, pix % W) + c0 + g * 8, f);
+        float4* d = reinterpret_cast<float4*>(A + pix * chk + g * 8);
+        d[0] = make_float4(f[0], f[1], f[2], f[3]); d[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    __syncthreads();
+    const int items4 = H * W * g4;
+    const DView outs[3] = {y5, y9, y13};
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        // row pass A -> Bf
+        for (int i = threadIdx.x; i < items4; i += blockDim.x) {
+            const int g = i % g4, pix = i / g4, px = pix % W;
+            float4 m = *reinterpret_cast<const float4*>(A + pix * chk + g * 4);
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                if (d == 0 || px + d < 0 || px + d >= W) continue;
+                const float4 v = *reinterpret_cast<const float4*>(A + (pix + d) * chk + g * 4);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+            *reinterpret_cast<float4*>(Bf + pix * chk + g * 4) = m;
+        }
+        __syncthreads();
+        // column pass Bf -> A
+        for (int i = threadIdx.x; i < items4; i += blockDim.x) {
+            const int g = i % g4, pix = i / g4, py = pix / W;
+            float4 m = *reinterpret_cast<const float4*>(Bf + pix * chk + g * 4);
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                if (d == 0 || py + d < 0 || py + d >= H) continue;
+                const float4 v = *reinterpret_cast<const float4*>(Bf + (pix + d * W) * chk + g * 4);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+            *reinterpret_cast<float4*>(A + pix * chk + g * 4) = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < items8; i += blockDim.x) {
+            const int g = i % (chk / 8), pix = i / (chk / 8);
+            const float4* sp4 = reinterpret_cast<const float4*>(A + pix * chk + g * 8);
+            const float4 u = sp4[0], w = sp4[1];
+            const float f[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+            st8<T>(outs[lvl].ptr, dview_pix(outs[lvl], b, pix / W, pix % W) + c0 + g * 8, f);
+        }
+        // the next row pass only reads A, which is complete: no barrier needed before it
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -279,7 +458,13 @@ int launch_adown_prepool(const yre_view& x, const yre_view& lo, const yre_view& 
     // NB: kernel indexes its cell grid with (Ho,Wo) = (Gy,Gx); cells beyond hi's extent never
     // occur because Gy==Ho, Gx==Wo for every H,W >= 2.
     if (Gy != Ho || Gx != Wo) YRE_FAIL(YRE_EUNSUPPORTED, "adown: H=%d W=%d", x.H, x.W);
-    if (x.dtype == YRE_F32) adown_prepool_kernel<float><<<grid, 256, 0, s>>>(make_dview(x), make_dview(lo), make_dview(hi), Gy, Gx, half);
+    const int chn = x.dtype == YRE_F32 ? 32 : 64;      // 128 bytes of channels per CTA
+    if (half % chn == 0) {
+        const int tiles_x = yre_cdiv(Gx, AD_TX), tiles_y = yre_cdiv(Gy, AD_TY);
+        dim3 tg((unsigned)(tiles_x * tiles_y * x.B), (unsigned)(x.C / chn));
+        if (x.dtype == YRE_F32) adown_tiled_kernel<float><<<tg, 256, 0, s>>>(make_dview(x), make_dview(lo), make_dview(hi), half, tiles_x, tiles_y);
+        else adown_tiled_kernel<__nv_bfloat16><<<tg, 256, 0, s>>>(make_dview(x), make_dview(lo), make_dview(hi), half, tiles_x, tiles_y);
+    } else if (x.dtype == YRE_F32) adown_prepool_kernel<float><<<grid, 256, 0, s>>>(make_dview(x), make_dview(lo), make_dview(hi), Gy, Gx, half);
     else adown_prepool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(make_dview(x), make_dview(lo), make_dview(hi), Gy, Gx, half);
     YRE_LAUNCH_CHECK("adown_prepool");
     return YRE_OK;
@@ -292,6 +477,24 @@ int launch_spp_maxpool(const yre_view& x, const yre_view& y5, const yre_view& y9
         if (y->B != x.B || y->H != x.H || y->W != x.W || y->C != x.C || y->dtype != x.dtype || y->layout != YRE_NHWC)
             YRE_FAIL(YRE_EINVAL, "spp: output views must match the input");
     if (x.layout != YRE_NHWC) YRE_FAIL(YRE_EUNSUPPORTED, "spp: NHWC only");
+    // plane-resident kernel when a (2 x H x W x CHK) fp32 double buffer fits in shared memory
+    int chk = 0;
+    for (int c : {32, 16, 8})
+        if (x.C % c == 0 && (size_t)2 * x.H * x.W * c * sizeof(float) <= 96 * 1024) { chk = c; break; }
+    if (chk) {
+        const size_t smem = (size_t)2 * x.H * x.W * chk * sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done) {
+            YRE_CUDA(cudaFuncSetAttribute(spp_plane_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            YRE_CUDA(cudaFuncSetAttribute(spp_plane_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_done = true;
+        }
+        dim3 pg((unsigned)x.B, (unsigned)(x.C / chk));
+        if (x.dtype == YRE_F32) spp_plane_kernel<float><<<pg, 256, smem, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13), chk);
+        else spp_plane_kernel<__nv_bfloat16><<<pg, 256, smem, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13), chk);
+        YRE_LAUNCH_CHECK("spp_plane");
+        return YRE_OK;
+    }
     const long long total = (long long)x.B * x.H * x.W * (x.C / 8);
     dim3 grid(yre_cdiv(total, 256));
     if (x.dtype == YRE_F32) spp_kernel<float><<<grid, 256, 0, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13));

@@ -99,6 +99,147 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
     }
 }
 
+// ---- bf16 product variant: the same conv as a [pixels x 32] x [32 x 64] GEMM on mma.sync ------------
+// K = 9*Cin = 27 (zero-padded to 32) is too short for tcgen05 tiles and the layer is HBM-bound, so the
+// warp-level HMMA path is the right tool: a CTA stages the 3 input rows of one 64-pixel output row
+// segment in shared memory (coalesced fp32 reads), each warp builds the im2col A fragments of 16 pixels
+// on the fly, multiplies by the weights held in registers for the whole kernel, applies bias + SiLU and
+// writes its 16 x 64 bf16 tile through shared memory as full 16-byte, pixel-contiguous stores.
+constexpr int SM_PX = 16;       // output pixels per warp tile (one m16 MMA tile)
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, const uint32_t* b) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Warps are independent (no block barrier): each walks its own sequence of 16-pixel row segments,
+// and the global loads of segment n+1 are issued into registers before segment n is computed, so
+// the HBM latency hides behind the MMA + store work of the current segment.
+template <int STRIDE>
+__global__ void __launch_bounds__(128) stem_mma_kernel(const StemParams p, int segs, long long total_tiles) {
+    constexpr int NCOLS = SM_PX * STRIDE + 2;                    // input columns one segment needs
+    constexpr int PITCH = NCOLS + 1;
+    constexpr int NLD = (9 * NCOLS + 31) / 32;                   // loads per lane (Cin <= 3 -> 9 smem rows)
+    __shared__ float sin_all[4][9 * PITCH];                      // per warp: [ci*3+dy][input col]
+    __shared__ __align__(16) __nv_bfloat16 sout_all[4][16][64 + 8];  // per-warp output tile, 144-byte pitch
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float* sin = sin_all[warp];
+    __nv_bfloat16 (*sout)[72] = sout_all[warp];
+    const int K = 9 * p.Cin;                                     // <= 27
+    const int nrows = 3 * p.Cin;
+
+    // weights -> B fragments (held in registers for the whole kernel), bias
+    uint32_t bfrag[2][8][2];
+    float bias[8][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = j * 8 + g, k0 = ks * 16 + 2 * t + 8 * h;
+                const float w0 = k0 < K ? p.w[n * K + k0] : 0.f, w1 = (k0 + 1) < K ? p.w[n * K + k0 + 1] : 0.f;
+                bfrag[ks][j][h] = pack_bf16x2(w0, w1);
+            }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        bias[j][0] = p.bias ? p.bias[j * 8 + 2 * t] : 0.f;
+        bias[j][1] = p.bias ? p.bias[j * 8 + 2 * t + 1] : 0.f;
+    }
+    // smem offsets of the 8 im2col columns this thread contributes (k = tap*Cin + ci)
+    int aoff[2][2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = ks * 16 + 2 * t + 8 * h + e;
+                if (k < K) {
+                    const int tap = k / p.Cin, ci = k % p.Cin, dy = tap / 3, dx = tap % 3;
+                    aoff[ks][h][e] = (ci * 3 + dy) * PITCH + dx;
+                } else aoff[ks][h][e] = -1;
+            }
+
+    const long long wstride = (long long)gridDim.x * 4;
+    long long tile = (long long)blockIdx.x * 4 + warp;
+    float pre[NLD];
+
+    auto fetch = [&](long long tl) {                             // global -> registers for segment tl
+        const int seg = (int)(tl % segs);
+        const long long r = tl / segs;
+        const int oy = (int)(r % p.Ho), b = (int)(r / p.Ho);
+        const int ix0 = seg * SM_PX * STRIDE - 1;
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int i = lane + 32 * q;
+            const int row = i / NCOLS, col = i - row * NCOLS;
+            const int ci = row / 3, dy = row - 3 * ci;
+            const int iy = oy * STRIDE + dy - 1, ix = ix0 + col;
+            float v = 0.f;
+            if (row < nrows && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                v = __ldg(p.x + (((long long)b * p.Cin + ci) * p.H + iy) * p.W + ix);
+            pre[q] = v;
+        }
+    };
+
+    if (tile < total_tiles) fetch(tile);
+    for (; tile < total_tiles; tile += wstride) {
+        const int seg = (int)(tile % segs);
+        const long long r = tile / segs;
+        const int oy = (int)(r % p.Ho), b = (int)(r / p.Ho);
+        const int ox0 = seg * SM_PX;
+        __syncwarp();                                            // previous segment's smem readers are done
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int i = lane + 32 * q;
+            const int row = i / NCOLS, col = i - row * NCOLS;
+            if (i < 9 * NCOLS) sin[row * PITCH + col] = pre[q];
+        }
+        __syncwarp();
+        if (tile + wstride < total_tiles) fetch(tile + wstride); // in flight while this segment is computed
+
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j][0] = bias[j][0]; acc[j][1] = bias[j][1]; acc[j][2] = bias[j][0]; acc[j][3] = bias[j][1]; }
+        const int m0 = g * STRIDE, m1 = m0 + 8 * STRIDE;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t a[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int o0 = aoff[ks][h][0], o1 = aoff[ks][h][1];
+                const float v00 = o0 >= 0 ? sin[o0 + m0] : 0.f, v01 = o1 >= 0 ? sin[o1 + m0] : 0.f;
+                const float v10 = o0 >= 0 ? sin[o0 + m1] : 0.f, v11 = o1 >= 0 ? sin[o1 + m1] : 0.f;
+                a[2 * h + 0] = pack_bf16x2(v00, v01);            // row g
+                a[2 * h + 1] = pack_bf16x2(v10, v11);            // row g + 8
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_bf16_16816(acc[j], a, bfrag[ks][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (p.act == YRE_ACT_SILU) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[j][q] = silu_tanh(acc[j][q]);
+            }
+            *reinterpret_cast<uint32_t*>(&sout[g][j * 8 + 2 * t]) = pack_bf16x2(acc[j][0], acc[j][1]);
+            *reinterpret_cast<uint32_t*>(&sout[g + 8][j * 8 + 2 * t]) = pack_bf16x2(acc[j][2], acc[j][3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = lane + 32 * q, px = i >> 3, c16 = i & 7;
+            const int ox = ox0 + px;
+            if (ox < p.Wo) {
+                const uint4 v = *reinterpret_cast<const uint4*>(&sout[px][c16 * 8]);
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + dview_pix(p.y, b, oy, ox) + c16 * 8) = v;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
@@ -112,6 +253,19 @@ int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
     StemParams p;
     p.x = d.x_nchw; p.y = make_dview(d.y); p.w = d.w; p.bias = d.bias;
     p.B = d.B; p.Cin = d.Cin; p.H = d.H; p.W = d.W; p.Ho = Ho; p.Wo = Wo; p.Cout = d.y.C; p.stride = d.stride; p.act = d.act;
+    if (d.y.dtype == YRE_BF16 && d.Cin <= 3 && d.y.C == 64 && (reinterpret_cast<uintptr_t>(d.y.ptr) & 15) == 0) {
+        const int segs = yre_cdiv(Wo, SM_PX);
+        const long long tiles = (long long)d.B * Ho * segs;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long want = (tiles + 3) / 4;
+        const unsigned grid = (unsigned)(want < (long long)sms * 4 ? want : (long long)sms * 4);
+        if (d.stride == 2) stem_mma_kernel<2><<<grid, 128, 0, s>>>(p, segs, tiles);
+        else stem_mma_kernel<1><<<grid, 128, 0, s>>>(p, segs, tiles);
+        YRE_LAUNCH_CHECK("stem_mma");
+        return YRE_OK;
+    }
     const long long total = (long long)d.B * Ho * ((Wo + PX - 1) / PX);
     const size_t smem = (size_t)(9 * d.Cin + 1) * d.y.C * sizeof(float);
     if (smem > 48 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "stem: Cout too large for the weight cache");

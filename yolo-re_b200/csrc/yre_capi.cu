@@ -262,7 +262,11 @@ int yre_plan_rebind(yre_plan* p, const void* old_ptr, void* new_ptr) {
             case OP_CONV_TC:
                 if (o.conv.x.ptr == old_ptr || o.conv.w == old_ptr)
                     YRE_FAIL(YRE_EUNSUPPORTED, "plan_rebind: buffer is baked into a TMA tensor map");
-                n += conv_tc_rebind(o.tc, old_ptr, new_ptr);
+                {
+                    const int r = conv_tc_rebind(o.tc, old_ptr, new_ptr);
+                    if (r < 0) YRE_FAIL(YRE_EUNSUPPORTED, "plan_rebind: buffer is baked into a TMA tensor map");
+                    n += r;
+                }
                 fix(o.conv.y.ptr); fix(o.conv.res.ptr);
                 break;
             case OP_CONV_FFMA:

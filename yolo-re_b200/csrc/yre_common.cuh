@@ -86,17 +86,39 @@ template <> __device__ __forceinline__ void st4<__nv_bfloat16>(void* p, long lon
     *reinterpret_cast<uint2*>((__nv_bfloat16*)p + i) = u;
 }
 
-// 8 consecutive channels as fp32
-template <typename T> __device__ __forceinline__ void ld8(const void* p, long long i, float* o) {
-    float4 a = ld4<T>(p, i), b = ld4<T>(p, i + 4);
+// 8 consecutive channels as fp32 (index i multiple of 8 elements: one 16-byte access for bf16, two for fp32)
+template <typename T> __device__ __forceinline__ void ld8(const void* p, long long i, float* o);
+template <> __device__ __forceinline__ void ld8<float>(const void* p, long long i, float* o) {
+    const float4 a = *reinterpret_cast<const float4*>((const float*)p + i), b = *reinterpret_cast<const float4*>((const float*)p + i + 4);
     o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
-template <typename T> __device__ __forceinline__ void st8(void* p, long long i, const float* o) {
-    st4<T>(p, i, make_float4(o[0], o[1], o[2], o[3]));
-    st4<T>(p, i + 4, make_float4(o[4], o[5], o[6], o[7]));
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const void* p, long long i, float* o) {
+    const uint4 u = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)p + i);
+    o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+    o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+    o[4] = __uint_as_float(u.z << 16); o[5] = __uint_as_float(u.z & 0xffff0000u);
+    o[6] = __uint_as_float(u.w << 16); o[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+template <typename T> __device__ __forceinline__ void st8(void* p, long long i, const float* o);
+template <> __device__ __forceinline__ void st8<float>(void* p, long long i, const float* o) {
+    *reinterpret_cast<float4*>((float*)p + i) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>((float*)p + i + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(void* p, long long i, const float* o) {
+    uint4 u;
+    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>((__nv_bfloat16*)p + i) = u;
 }
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// SiLU with ONE MUFU op: x*sigmoid(x) = 0.5x*(1 + tanh(0.5x)); tanh.approx is good to ~2^-11 relative,
+// far inside bf16's 2^-8 -- used wherever the result is rounded to bf16 anyway.
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 // ---- op launchers implemented in the k_*.cu files (host side, used by the C API and the plan) -----
 struct ConvTcPlan;   // pre-encoded tensor maps + tile config of one tcgen05 conv (k_conv_tc.cu)
