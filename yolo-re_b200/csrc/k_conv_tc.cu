@@ -46,7 +46,7 @@ struct TcParams {
     int Ho, Wo, B;
     int taps, kchunks, block_k, block_n, stages;
     int phase4;                     // stride-2 conv reading parity planes
-    int x_coff, Cin;
+    int x_coff, Cin, Cout;
     uint32_t a_bytes, b_bytes;
     uint32_t sbo16;                 // stride-byte-offset >> 4 of the smem descriptors
     uint32_t layout_type;           // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
@@ -57,6 +57,7 @@ struct TcParams {
     const void* res; int res_f32; int res_ctot, res_coff;
     int* dbg;                       // optional watchdog record (may be null)
     int tma_store;                  // 1: bf16 output through the smem-staged TMA store
+    int npipes;                     // 1 or 2 (producer, MMA) warp pairs
     int stw, sth, stb;              // the 32 pixels of one TMEM lane quarter as a (stb x sth x stw) sub-patch
     uint32_t stage_out_bytes;       // bytes of one per-warp staging buffer (32 rows x 32 ch x 2 = 2048)
 };
@@ -138,11 +139,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// descriptors are passed as (low word, shared high word): only the 14-bit start address in the low word
+// changes per stage / K step, which keeps the issue loop on 32-bit arithmetic
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -175,6 +179,22 @@ __device__ __forceinline__ float silu_fast(float x) {
     return fmaf(h, t, h);
 }
 
+// Tile cursor: (nt, xt, yt, bt) of tile index t, advanced by a constant stride without div/mod.
+struct TileCur {
+    int nt, xt, yt, bt;
+    int dn, dx, dy, db;      // digits of the stride
+    __device__ __forceinline__ void init(const TcParams& p, int t, int stride) {
+        nt = t % p.tiles_n; int m = t / p.tiles_n; xt = m % p.tiles_x; m /= p.tiles_x; yt = m % p.tiles_y; bt = m / p.tiles_y;
+        dn = stride % p.tiles_n; m = stride / p.tiles_n; dx = m % p.tiles_x; m /= p.tiles_x; dy = m % p.tiles_y; db = m / p.tiles_y;
+    }
+    __device__ __forceinline__ void step(const TcParams& p) {
+        nt += dn; int c = nt >= p.tiles_n; nt -= c ? p.tiles_n : 0;
+        xt += dx + c; c = xt >= p.tiles_x; xt -= c ? p.tiles_x : 0;
+        yt += dy + c; c = yt >= p.tiles_y; yt -= c ? p.tiles_y : 0;
+        bt += db + c;
+    }
+};
+
 // optional timeline trace (YRE_TC_TRACE=1): CTA 0 records (role, event, clock) triples
 __device__ __forceinline__ void trace(int* dbg, int role, int& n, int ev) {
     if (dbg && blockIdx.x == 0 && n < 96) {
@@ -196,22 +216,30 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
     return d;
 }
 
-// epilogue math for NC accumulator columns [n, n+NC): +bias -> SiLU -> (+residual), result in f[]
+// epilogue math for NC accumulator columns [n, n+NC): +bias -> SiLU -> (+residual), result in f[].
+// `sbias` = shared-memory copy of the bias vector (whole Cout); packed fp32x2 ops (FADD2/FMUL2/FFMA2) halve
+// the FP issue slots, SiLU costs one MUFU.TANH per element.
 template <int NC>
-__device__ __forceinline__ void epilogue_math(const TcParams& p, const uint32_t* v, float* f, bool valid, long long pix, int n) {
+__device__ __forceinline__ void epilogue_math(const TcParams& p, const float* sbias, const uint32_t* v, float* f, bool valid, long long pix, int n) {
+    float2 x2[NC / 2];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) f[i] = __uint_as_float(v[i]);
-    if (p.bias) {
-#pragma unroll
-        for (int i = 0; i < NC; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
-        }
+    for (int i = 0; i < NC; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + n + i);
+        x2[i / 2] = __fadd2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(b4.x, b4.y));
+        x2[i / 2 + 1] = __fadd2_rn(make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), make_float2(b4.z, b4.w));
     }
     if (p.act == YRE_ACT_SILU) {
 #pragma unroll
-        for (int i = 0; i < NC; ++i) f[i] = silu_fast(f[i]);
+        for (int i = 0; i < NC / 2; ++i) {
+            const float2 h = __fmul2_rn(x2[i], make_float2(0.5f, 0.5f));
+            float2 t;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
+            x2[i] = __ffma2_rn(h, t, h);
+        }
     }
+#pragma unroll
+    for (int i = 0; i < NC / 2; ++i) { f[2 * i] = x2[i].x; f[2 * i + 1] = x2[i].y; }
     if (p.res && valid) {
         if (p.res_f32) {
             const float* r = reinterpret_cast<const float*>(p.res) + pix * p.res_ctot + p.res_coff + n;
@@ -265,6 +293,7 @@ __device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base
     }
 }
 
+template <int KSTEPS>     // BLOCK_K / 16: 4 (128-byte swizzle) or 2 (64-byte swizzle)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TcParams p) {
@@ -278,6 +307,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // barrier i at bar_base + 8*i : full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4)
     const uint32_t tmem_slot = bar_base + 8u * (2u * S + 4u);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    float* sbias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - raw));     // [Cout] bias copy (zeros if none)
+    for (int i = threadIdx.x; i < p.Cout; i += NUM_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -302,17 +333,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // local tiles j with (j & 1) == pipe, owns half of the shared-memory stage ring and accumulator buffer
     // `pipe`.  One issuing thread needs ~600 cycles per k-iteration (mbarrier wait + descriptor math on the
     // uniform datapath + commit); two of them keep the tensor pipe and the TMA unit fed.
-    const uint32_t S2 = S >> 1;
-    if (warp == 0 || warp == 2) {
+    const uint32_t NP = (uint32_t)p.npipes;
+    const uint32_t S2 = S / NP;
+    if ((warp == 0 || warp == 2) && (uint32_t)(warp >> 1) < NP) {
         // ================= TMA producer (whole warp runs the loop, one elected lane issues) =================
         const uint32_t pipe = (uint32_t)warp >> 1;
         uint32_t stage = 0, phase = 0;
         int tn = 0;
-        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += 2 * gridDim.x) {
-            const int nt = t % p.tiles_n; int mt = t / p.tiles_n;
-            const int xt = mt % p.tiles_x; mt /= p.tiles_x;
-            const int yt = mt % p.tiles_y; const int bt = mt / p.tiles_y;
-            const int x0 = xt * p.tw, y0 = yt * p.th, b0 = bt * p.tb, n0 = nt * p.block_n;
+        TileCur tc;
+        tc.init(p, blockIdx.x + (int)pipe * gridDim.x, (int)(NP * gridDim.x));
+        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += (int)(NP * gridDim.x), tc.step(p)) {
+            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt * p.tb, n0 = tc.nt * p.block_n;
             for (int tap = 0; tap < p.taps; ++tap) {
                 int dx = 0, dy = 0, plane = 0;
                 if (p.taps == 9) {
@@ -341,16 +372,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1 || warp == 3) {
+    } else if ((warp == 1 || warp == 3) && (uint32_t)(warp >> 1) < NP) {
         // ================= MMA issuer (warp-uniform loop, elected lane issues) =================
         const uint32_t pipe = (uint32_t)warp >> 1;
-        uint32_t stage = 0, phase = 0, acc_phase = 0;
-        const int ksteps = p.block_k >> 4;
+        uint32_t stage = 0, phase = 0;
         const uint64_t desc0 = make_smem_desc(0, p.sbo16, p.layout_type);
-        const uint32_t tfull = bar_base + 8u * (2u * S + pipe), tempty = bar_base + 8u * (2u * S + 2u + pipe);
-        const uint32_t d_tmem = tmem_base + pipe * ACC_STRIDE;
+        const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
+        const uint32_t stage16 = stage_bytes >> 4, a16 = p.a_bytes >> 4;
+        const uint32_t ring_lo = desc_lo0 + ((sbase + pipe * S2 * stage_bytes) >> 4);   // smem < 256 KB: no overflow of the 14-bit field
         int tn = 0;
-        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += 2 * gridDim.x) {
+        uint32_t j = pipe;                               // local tile counter: accumulator j&1, phase (j>>1)&1
+        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += (int)(NP * gridDim.x), j += NP) {
+            const uint32_t acc = j & 1u, acc_phase = (j >> 1) & 1u;
+            const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 2u + acc);
+            const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
             mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
             tc_fence_after();
             if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 10);
@@ -361,11 +396,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 11);
                 if (elect_one()) {
-                    const uint32_t sa = sbase + gs * stage_bytes, sb = sa + p.a_bytes;
-                    const uint64_t da = desc0 | (uint64_t)((sa >> 4) & 0x3FFFu);
-                    const uint64_t db = desc0 | (uint64_t)((sb >> 4) & 0x3FFFu);
-                    for (int k = 0; k < ksteps; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the >>4 address field
-                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (it | k) ? 1u : 0u);
+                    const uint32_t a_lo = ring_lo + stage * stage16, b_lo = a_lo + a16;
+                    umma_bf16(d_tmem, a_lo, b_lo, desc_hi, p.idesc, it > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int k = 1; k < KSTEPS; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the >>4 address field
+                        umma_bf16(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, 1u);
                     umma_commit(empty);                       // frees the smem stage when these MMAs retire
                     if (it == kiters - 1) umma_commit(tfull); // accumulator complete -> epilogue
                 }
@@ -373,7 +408,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 12);
                 if (++stage == S2) { stage = 0; phase ^= 1u; }
             }
-            acc_phase ^= 1u;
         }
     } else if (warp >= 4) {
         // ================= epilogue (8 warps, warp-local: no CTA barrier) =================
@@ -389,11 +423,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nchunks = (p.block_n + 31) >> 5;
         uint32_t acc = 0, acc_phase = 0, obuf = 0;
         int tn = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-            const int nt = t % p.tiles_n; int mt = t / p.tiles_n;
-            const int xt = mt % p.tiles_x; mt /= p.tiles_x;
-            const int yt = mt % p.tiles_y; const int bt = mt / p.tiles_y;
-            const int x0 = xt * p.tw, y0 = yt * p.th, b0 = bt * p.tb, n0 = nt * p.block_n;
+        TileCur tc;
+        tc.init(p, blockIdx.x, (int)gridDim.x);
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, tc.step(p)) {
+            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt * p.tb, n0 = tc.nt * p.block_n;
             const int x = x0 + xx, y = y0 + yy, b = b0 + bi;
             const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
             const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
@@ -419,7 +452,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     have = (cn < nchunks && cn * 32 + 32 <= p.block_n);
                     if (have) TMEM_LD32(taddr + (uint32_t)(cn * 32), v);
                     float f[32];
-                    epilogue_math<32>(p, w, f, valid, pix, n0 + col);
+                    epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col);
                     if (p.tma_store) {
                         if (lane == 0) bulk_wait_read<1>();      // the store that used this buffer two chunks ago has read it
                         __syncwarp();
@@ -440,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float f[16];
                     TMEM_LD16(taddr + (uint32_t)col, w16);
                     tmem_ld_wait();
-                    epilogue_math<16>(p, w16, f, valid, pix, n0 + col);
+                    epilogue_math<16>(p, sbias, w16, f, valid, pix, n0 + col);
                     if (valid) store_direct<16>(p, f, pix, n0 + col);
                 }
             }
@@ -527,7 +560,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     memset(pl, 0, sizeof(*pl));
     TcParams& p = pl->p;
     const int Cin = d.x.C, Cout = d.y.C, Ho = d.y.H, Wo = d.y.W, B = d.y.B;
-    p.Ho = Ho; p.Wo = Wo; p.B = B; p.Cin = Cin; p.x_coff = d.x.c_off;
+    p.Ho = Ho; p.Wo = Wo; p.B = B; p.Cin = Cin; p.Cout = Cout; p.x_coff = d.x.c_off;
     p.taps = d.k * d.k;
     p.phase4 = d.stride == 2;
     p.block_k = (Cin % 64 == 0) ? 64 : 32;
@@ -569,15 +602,20 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     p.stw = p.tw < 32 ? p.tw : 32;
     p.sth = (32 / p.stw) < p.th ? (32 / p.stw) : p.th;
     p.stb = 32 / (p.stw * p.sth);
-    const uint32_t smem_cap = 227u * 1024u - 1024u - 256u;          // alignment slack + barriers
+    const uint32_t smem_cap = 227u * 1024u - 1024u - 256u - (uint32_t)Cout * 4u;   // alignment slack + barriers + bias copy
     int stages = (int)((smem_cap - 16u * p.stage_out_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
     const int force_st = env_int("YRE_TC_STAGES", 0);
-    if (force_st >= 4 && force_st <= stages) stages = force_st;
-    stages &= ~1;                                                    // two pipelines share the ring
-    if (stages < 4) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: tile does not fit shared memory"); }
+    if (force_st >= 2 && force_st <= stages) stages = force_st;
+    if (stages < 2) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: tile does not fit shared memory"); }
+    // two (producer, MMA) pairs when the ring is deep enough to give each at least 3 stages; big-stage
+    // (compute-bound) tiles keep one pair with the whole ring, which hides the TMA latency better
+    p.npipes = stages >= 6 ? 2 : 1;
+    const int force_np = env_int("YRE_TC_PIPES", 0);
+    if (force_np == 1 || (force_np == 2 && stages >= 4)) p.npipes = force_np;
+    if (p.npipes == 2) stages &= ~1;
     p.stages = stages;
-    pl->smem = (size_t)stages * stage_bytes + 16 * p.stage_out_bytes + 8 * (2 * stages + 4) + 16 + 1024;
+    pl->smem = (size_t)stages * stage_bytes + 16 * p.stage_out_bytes + 8 * (2 * stages + 4) + 32 + (size_t)Cout * 4 + 1024;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     p.bias = d.bias; p.act = d.act;
     p.y = d.y.ptr; p.y_f32 = d.y.dtype == YRE_F32; p.y_ctot = d.y.C_total; p.y_coff = d.y.c_off;
@@ -641,10 +679,12 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    conv_tc_kernel<<<pl->grid, NUM_THREADS, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+    if (pl->p.block_k == 64) conv_tc_kernel<4><<<pl->grid, NUM_THREADS, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+    else conv_tc_kernel<2><<<pl->grid, NUM_THREADS, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
     YRE_LAUNCH_CHECK("conv_tc");
     return YRE_OK;
 }

@@ -56,13 +56,15 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams p) {
         s_ax[tid] = (float)px + 0.5f; s_ay[tid] = (float)py + 0.5f; s_st[tid] = p.stride[l];
     }
     __syncthreads();
-    // ---- stage raw rows (coalesced 4-channel chunks) ----
+    // ---- stage raw rows: warp w takes anchors w, w+4, ...; a row (CH floats) is one contiguous burst ----
     const int chunks = CH / 4;
-    for (int i = tid; i < na * chunks; i += blockDim.x) {
-        const int al = i / chunks, ck = i - al * chunks;
+    const int wid = tid >> 5, lane = tid & 31;
+    for (int al = wid; al < na; al += 4) {
         const long long src = s_src[al];
-        const float4 q = ld4<T>(p.raw[(int)(src >> 56)].ptr, (src & 0x00ffffffffffffffll) + ck * 4);
-        *reinterpret_cast<float4*>(s_raw + al * PITCH + ck * 4) = q;
+        const void* base = p.raw[(int)(src >> 56)].ptr;
+        const long long off = src & 0x00ffffffffffffffll;
+        for (int ck = lane; ck < chunks; ck += 32)
+            *reinterpret_cast<float4*>(s_raw + al * PITCH + ck * 4) = ld4<T>(base, off + ck * 4);
     }
     __syncthreads();
 
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams p) {
             float den = 0.f, num = 0.f;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const float e = expf(v[k] - mx);
+                const float e = __expf(v[k] - mx);
                 den += e;
                 num = fmaf(e, p.dfl_w[k], num);
             }
@@ -103,12 +105,10 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams p) {
         o[2] = (x2 - x1) * st;
         o[3] = (y2 - y1) * st;
     }
-    // ---- class scores ----
-    for (int i = tid; i < na * p.nc; i += blockDim.x) {
-        const int al = i / p.nc, c = i % p.nc;
-        const float z = s_raw[al * PITCH + 64 + c];
-        s_out[al * OC + 4 + c] = 1.0f / (1.0f + expf(-z));
-    }
+    // ---- class scores: warp per anchor, lanes stride the classes (no div/mod) ----
+    for (int al = wid; al < na; al += 4)
+        for (int c = lane; c < p.nc; c += 32)
+            s_out[al * OC + 4 + c] = __frcp_rn(1.0f + __expf(-s_raw[al * PITCH + 64 + c]));
     __syncthreads();
 
     // ---- contiguous coalesced store of na*OC floats ----

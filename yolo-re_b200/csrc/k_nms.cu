@@ -153,6 +153,8 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const flo
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
+    // inter == 0 -> IoU is +-0 or NaN, neither exceeds a threshold >= 0: skip the IEEE division (exact shortcut)
+    if (inter == 0.f && thr >= 0.0) return false;
     const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
     return (double)iou > thr;
 }
@@ -240,19 +242,29 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
         if ((tid & 31) == 0) alive_w[tid >> 5] = bal;
         __syncthreads();
         // ---- 3. in-chunk suppression bitmask (row i: later boxes j>i it would suppress) ----
-        if (alive) {
-            for (int w = 0; w < CW; ++w) {
-                u64 bits = 0ull;
-                const int j0 = w * 64;
-                if (j0 + 63 > tid && j0 < cnt) {
-                    const int jend = min(64, cnt - j0);
-                    for (int jj = max(0, tid + 1 - j0); jj < jend; ++jj) {
-                        const int j = j0 + jj;
-                        if (!((alive_w[j >> 5] >> (j & 31)) & 1u)) continue;
-                        if (iou_gt(mine, marea, cbox[j], carea[j], p.iou)) bits |= 1ull << jj;
+        // rows are dealt round-robin to the 16 warps; the 32 lanes of a warp test 32 columns at a time and a
+        // ballot yields the mask bits -- balanced work (the old one-thread-per-row loop left thread 0 with 511
+        // IoUs and thread 511 with none) and conflict-free shared-memory reads.
+        {
+            const int wid = tid >> 5, ln = tid & 31;
+            for (int i = wid; i < cnt; i += CHUNK / 32) {
+                if (!((alive_w[i >> 5] >> (i & 31)) & 1u)) continue;          // warp-uniform
+                const float4 bi = cbox[i];
+                const float ai = carea[i];
+                for (int w = i >> 6; w < CW; ++w) {
+                    unsigned lo_bits = 0u, hi_bits = 0u;
+                    if (w * 64 < cnt) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int j = w * 64 + h * 32 + ln;
+                            bool sup = false;
+                            if (j > i && j < cnt && ((alive_w[j >> 5] >> (j & 31)) & 1u)) sup = iou_gt(bi, ai, cbox[j], carea[j], p.iou);
+                            const unsigned bal2 = __ballot_sync(0xffffffffu, sup);
+                            if (h == 0) lo_bits = bal2; else hi_bits = bal2;
+                        }
                     }
+                    if (ln == 0) mask[(size_t)i * CW + w] = (u64)lo_bits | ((u64)hi_bits << 32);
                 }
-                mask[(size_t)tid * CW + w] = bits;
             }
         }
         __syncthreads();

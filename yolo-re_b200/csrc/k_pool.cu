@@ -332,18 +332,27 @@ __global__ void __launch_bounds__(256) spp_plane_kernel(DView x, DView y5, DView
 // K5: nearest x2 (reference: nn.Upsample, parser.py:159-171) written into the consumer's slice
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_kernel(DView x, DView y) {
+    // one thread per INPUT (pixel, 8-channel group): one 16-byte load feeds the four output pixels
     const int groups = x.C / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)y.B * y.H * y.W * groups;
+    const long long total = (long long)x.B * x.H * x.W * groups;
     if (idx >= total) return;
     const int c = (int)(idx % groups) * 8;
     long long t = idx / groups;
-    const int ox = (int)(t % y.W); t /= y.W;
-    const int oy = (int)(t % y.H);
-    const int b = (int)(t / y.H);
+    const int ix = (int)(t % x.W); t /= x.W;
+    const int iy = (int)(t % x.H);
+    const int b = (int)(t / x.H);
     float v[8];
-    ld8<T>(x.ptr, dview_pix(x, b, oy >> 1, ox >> 1) + c, v);
-    st8<T>(y.ptr, dview_pix(y, b, oy, ox) + c, v);
+    ld8<T>(x.ptr, dview_pix(x, b, iy, ix) + c, v);
+    if (y.layout == YRE_NHWC) {
+        const long long o = dview_pix(y, b, 2 * iy, 2 * ix) + c;
+        const long long rs = (long long)y.W * y.C_total;
+        st8<T>(y.ptr, o, v); st8<T>(y.ptr, o + y.C_total, v);
+        st8<T>(y.ptr, o + rs, v); st8<T>(y.ptr, o + rs + y.C_total, v);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) st8<T>(y.ptr, dview_pix(y, b, 2 * iy + (q >> 1), 2 * ix + (q & 1)) + c, v);
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -507,7 +516,7 @@ int launch_upsample2x(const yre_view& x, const yre_view& y, cudaStream_t s) {
     if (check8(x, "upsample.x") || check8(y, "upsample.y")) return YRE_EINVAL;
     if (y.B != x.B || y.H != 2 * x.H || y.W != 2 * x.W || y.C != x.C || y.dtype != x.dtype)
         YRE_FAIL(YRE_EINVAL, "upsample2x: output must be 2x the input");
-    const long long total = (long long)y.B * y.H * y.W * (y.C / 8);
+    const long long total = (long long)x.B * x.H * x.W * (x.C / 8);
     dim3 grid(yre_cdiv(total, 256));
     if (x.dtype == YRE_F32) upsample2x_kernel<float><<<grid, 256, 0, s>>>(make_dview(x), make_dview(y));
     else upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(make_dview(x), make_dview(y));

@@ -117,7 +117,7 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, cons
 // and the global loads of segment n+1 are issued into registers before segment n is computed, so
 // the HBM latency hides behind the MMA + store work of the current segment.
 template <int STRIDE>
-__global__ void __launch_bounds__(128) stem_mma_kernel(const StemParams p, int segs, long long total_tiles) {
+__global__ void __launch_bounds__(128, 4) stem_mma_kernel(const StemParams p, int segs, long long total_tiles) {
     constexpr int NCOLS = SM_PX * STRIDE + 2;                    // input columns one segment needs
     constexpr int PITCH = NCOLS + 1;
     constexpr int NLD = (9 * NCOLS + 31) / 32;                   // loads per lane (Cin <= 3 -> 9 smem rows)
