@@ -273,6 +273,18 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- NMS device time (3 launches: init, filter, select) ----
+    y_static, _ = model(x_dev)
+    pred_static = y_static.permute(0, 2, 1)
+    torch.cuda.synchronize(dev)
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for _ in range(5):
+        nms_raw(pred_static, CONF, IOU, MAX_DET)
+    n1.record()
+    torch.cuda.synchronize(dev)
+    nms_ms = n0.elapsed_time(n1) / 5
+
     # ---- per-op device timing: roofline of the conv kernels (rank 0) ----
     table = plan.op_table()
     n_ops = len(table)
@@ -307,6 +319,12 @@ def main():
                 "launches_per_step": cf["launches"], "ms_per_step": cf["ms"], "flops_per_step": cf["flops"],
                 "flops_per_image_folded_graph": all_conv_flops / Bn}
     stage_ms = {n: round(f["ms"], 4) for n, f in fam.items()}
+    stage_ms["nms"] = round(nms_ms, 4)
+    # HBM-bound stages against the measured copy bandwidth (algorithmic bytes)
+    A = sum((IMG // s_) ** 2 for s_ in (8, 16, 32))
+    dec_bytes = Bn * A * (144 * 4 + 84 * 4)
+    hbm = {"dfl_decode_score": {"bytes": dec_bytes, "GBps": dec_bytes / (fam["dfl_decode_score"]["ms"] / 1e3) / 1e9,
+                                "frac_of_measured_hbm": dec_bytes / (fam["dfl_decode_score"]["ms"] / 1e3) / 1e9 / peak_gbs}}
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample ----
     cpu = None
@@ -333,7 +351,7 @@ def main():
                 "how": "pinned host fp32 batch -> H2D (copy stream, double-buffered) -> YOLO.forward -> nms -> D2H detections"},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "tcgen05_convs_per_step": plan.num_tcgen05,
-        "roofline": roofline, "stage_ms_per_step": stage_ms, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "stage_ms_per_step": stage_ms, "hbm_stages": hbm, "cpu_baseline": cpu, "clocks": clocks,
     }))
     if dist is not None:
         dist.barrier()

@@ -14,7 +14,8 @@
 
 namespace {
 
-constexpr int TILE = 32;
+constexpr int TILE = 8;        // anchors per WARP; warps are independent (no block barrier anywhere)
+constexpr int WARPS = 4;
 constexpr int MAXL = 8;
 
 struct DecodeParams {
@@ -27,50 +28,67 @@ struct DecodeParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(128) decode_kernel(const DecodeParams p) {
+__global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float sm[];
     const int CH = 64 + p.nc;               // floats per raw row
     const int PITCH = CH + 4;               // keeps 16B alignment, skews banks
     const int OC = 4 + p.nc;
-    float* s_raw = sm;                      // [TILE][PITCH]
-    float* s_e = s_raw + TILE * PITCH;      // [TILE][4]
-    float* s_out = s_e + TILE * 4;          // [TILE][OC]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s_raw = sm + warp * (TILE * PITCH + TILE * OC);   // [TILE][PITCH]
+    float* s_out = s_raw + TILE * PITCH;                      // [TILE][OC]
 
     const int tiles_per_img = (p.A + TILE - 1) / TILE;
-    const int b = blockIdx.x / tiles_per_img;
-    const int a0 = (blockIdx.x % tiles_per_img) * TILE;
+    const long long wt = (long long)blockIdx.x * WARPS + warp;
+    if (wt >= (long long)tiles_per_img * p.B) return;
+    const int b = (int)(wt / tiles_per_img);
+    const int a0 = (int)(wt % tiles_per_img) * TILE;
     const int na = min(TILE, p.A - a0);
-    const int tid = threadIdx.x;
 
-    // ---- per-anchor source offset (level lookup + div/mod once per anchor, not once per load) ----
-    __shared__ long long s_src[TILE];
-    __shared__ float s_ax[TILE], s_ay[TILE], s_st[TILE];
-    if (tid < na) {
-        const int a = a0 + tid;
+    // ---- per-anchor source (lanes 0..TILE-1 own one anchor each; broadcast by shuffle) ----
+    long long my_src = 0; int my_lvl = 0; float my_ax = 0.f, my_ay = 0.f, my_st = 0.f;
+    if (lane < na) {
+        const int a = a0 + lane;
         int l = 0;
         while (l + 1 < p.levels && a >= p.a_start[l + 1]) ++l;
         const int r = a - p.a_start[l];
-        const DView& v = p.raw[l];
-        const int py = r / v.W, px = r - py * v.W;
-        s_src[tid] = dview_pix(v, b, py, px) | ((long long)l << 56);
-        s_ax[tid] = (float)px + 0.5f; s_ay[tid] = (float)py + 0.5f; s_st[tid] = p.stride[l];
+        const int W = p.raw[l].W;
+        const int py = r / W, px = r - py * W;
+        my_src = dview_pix(p.raw[l], b, py, px); my_lvl = l;
+        my_ax = (float)px + 0.5f; my_ay = (float)py + 0.5f; my_st = p.stride[l];
     }
-    __syncthreads();
-    // ---- stage raw rows: warp w takes anchors w, w+4, ...; a row (CH floats) is one contiguous burst ----
+    // ---- stage the raw rows: flat 16-byte chunks over the tile, every lane busy ----
     const int chunks = CH / 4;
-    const int wid = tid >> 5, lane = tid & 31;
-    for (int al = wid; al < na; al += 4) {
-        const long long src = s_src[al];
-        const void* base = p.raw[(int)(src >> 56)].ptr;
-        const long long off = src & 0x00ffffffffffffffll;
-        for (int ck = lane; ck < chunks; ck += 32)
-            *reinterpret_cast<float4*>(s_raw + al * PITCH + ck * 4) = ld4<T>(base, off + ck * 4);
+    // All loads of a lane are issued back to back into registers BEFORE the first shared-memory store: a
+    // load -> store -> load loop would serialise one HBM round trip per chunk (that alone made the first
+    // version of this kernel ~3x slower than its bandwidth bound).
+    constexpr int MAXQ = 16;                                  // covers TILE * chunks <= 512, i.e. nc <= 192
+    const int total = na * chunks;
+    for (int base0 = 0; base0 < total; base0 += 32 * MAXQ) {
+        float4 buf[MAXQ];
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+            const int i = base0 + q * 32 + lane;
+            const bool act = i < total;
+            const int al = act ? i / chunks : 0, ck = i - al * chunks;
+            const long long src = __shfl_sync(0xffffffffu, my_src, al);
+            const int lvl = __shfl_sync(0xffffffffu, my_lvl, al);
+            if (act) buf[q] = ld4<T>(p.raw[lvl].ptr, src + ck * 4);
+        }
+#pragma unroll
+        for (int q = 0; q < MAXQ; ++q) {
+            const int i = base0 + q * 32 + lane;
+            if (i < total) {
+                const int al = i / chunks, ck = i - al * chunks;
+                *reinterpret_cast<float4*>(s_raw + al * PITCH + ck * 4) = buf[q];
+            }
+        }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- DFL expectation: thread = (anchor, side) ----
+    // ---- DFL expectation: lane = (anchor, side) ----
+    float e = 0.f;
     {
-        const int al = tid >> 2, side = tid & 3;
+        const int al = lane >> 2, side = lane & 3;
         if (al < na) {
             const float* z = s_raw + al * PITCH + side * 16;
             float v[16];
@@ -85,40 +103,41 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams p) {
             float den = 0.f, num = 0.f;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const float e = __expf(v[k] - mx);
-                den += e;
-                num = fmaf(e, p.dfl_w[k], num);
+                const float ex = __expf(v[k] - mx);
+                den += ex;
+                num = fmaf(ex, p.dfl_w[k], num);
             }
-            s_e[al * 4 + side] = num / den;
+            e = num / den;
         }
     }
-    __syncthreads();
-
-    // ---- boxes: thread = anchor ----
-    if (tid < na) {
-        const float ax = s_ax[tid], ay = s_ay[tid], st = s_st[tid];
-        const float x1 = ax - s_e[tid * 4 + 0], y1 = ay - s_e[tid * 4 + 1];
-        const float x2 = ax + s_e[tid * 4 + 2], y2 = ay + s_e[tid * 4 + 3];
-        float* o = s_out + tid * OC;
-        o[0] = ((x1 + x2) / 2.f) * st;
-        o[1] = ((y1 + y2) / 2.f) * st;
-        o[2] = (x2 - x1) * st;
-        o[3] = (y2 - y1) * st;
+    // ---- boxes: lane a (< TILE) gathers its four sides from lanes 4a..4a+3 ----
+    {
+        const int src0 = (lane & 7) * 4;
+        const float e0 = __shfl_sync(0xffffffffu, e, src0), e1 = __shfl_sync(0xffffffffu, e, src0 + 1);
+        const float e2 = __shfl_sync(0xffffffffu, e, src0 + 2), e3 = __shfl_sync(0xffffffffu, e, src0 + 3);
+        if (lane < na) {
+            const float x1 = my_ax - e0, y1 = my_ay - e1, x2 = my_ax + e2, y2 = my_ay + e3;
+            float* o = s_out + lane * OC;
+            o[0] = ((x1 + x2) / 2.f) * my_st;
+            o[1] = ((y1 + y2) / 2.f) * my_st;
+            o[2] = (x2 - x1) * my_st;
+            o[3] = (y2 - y1) * my_st;
+        }
     }
-    // ---- class scores: warp per anchor, lanes stride the classes (no div/mod) ----
-    for (int al = wid; al < na; al += 4)
+    // ---- class scores: lanes stride the classes of each anchor (no div/mod) ----
+    for (int al = 0; al < na; ++al)
         for (int c = lane; c < p.nc; c += 32)
             s_out[al * OC + 4 + c] = __frcp_rn(1.0f + __expf(-s_raw[al * PITCH + 64 + c]));
-    __syncthreads();
+    __syncwarp();
 
     // ---- contiguous coalesced store of na*OC floats ----
     float* dst = p.y + ((long long)b * p.A + a0) * OC;
     const int nfl = na * OC;
-    if ((OC & 3) == 0) {
-        for (int i = tid; i < nfl / 4; i += blockDim.x)
+    if ((OC & 3) == 0 && ((a0 * OC) & 3) == 0) {
+        for (int i = lane; i < nfl / 4; i += 32)
             reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_out)[i];
     } else {
-        for (int i = tid; i < nfl; i += blockDim.x) dst[i] = s_out[i];
+        for (int i = lane; i < nfl; i += 32) dst[i] = s_out[i];
     }
 }
 
@@ -145,16 +164,16 @@ int launch_decode(const yre_decode_desc& d, cudaStream_t s) {
     p.A = A; p.B = d.raw[0].B;
     for (int k = 0; k < 16; ++k) p.dfl_w[k] = d.dfl_w[k];
     const int CH = 64 + d.nc, OC = 4 + d.nc;
-    const size_t smem = (size_t)(TILE * (CH + 4) + TILE * 4 + TILE * OC) * sizeof(float);
-    const int tiles = (A + TILE - 1) / TILE;
-    dim3 grid((unsigned)(tiles * p.B));
+    const size_t smem = (size_t)WARPS * (TILE * (CH + 4) + TILE * OC) * sizeof(float);
+    const long long tiles = (long long)((A + TILE - 1) / TILE) * p.B;
+    dim3 grid((unsigned)((tiles + WARPS - 1) / WARPS));
     if (smem > 200 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "decode: nc=%d too large for the staging tile", d.nc);
     if (smem > 48 * 1024) {
         YRE_CUDA(cudaFuncSetAttribute(decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         YRE_CUDA(cudaFuncSetAttribute(decode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (d.raw[0].dtype == YRE_F32) decode_kernel<float><<<grid, 128, smem, s>>>(p);
-    else decode_kernel<__nv_bfloat16><<<grid, 128, smem, s>>>(p);
+    if (d.raw[0].dtype == YRE_F32) decode_kernel<float><<<grid, WARPS * 32, smem, s>>>(p);
+    else decode_kernel<__nv_bfloat16><<<grid, WARPS * 32, smem, s>>>(p);
     YRE_LAUNCH_CHECK("dfl_decode_score");
     return YRE_OK;
 }

@@ -76,16 +76,28 @@ __global__ void __launch_bounds__(128) nms_filter_kernel(const FilterParams p) {
     const float4* base = reinterpret_cast<const float4*>(p.pred + ((size_t)b * p.A + a0) * (4 + p.nc));
 
     const bool vec = (p.nc & 3) == 0;        // rows are 16-byte aligned only when nc % 4 == 0
-    for (int idx = lane; vec && idx < na * n4; idx += 32) {
-        const int al = idx / n4, pos = idx % n4;
-        if (pos == 0) continue;
-        const float4 v = base[idx];
-        float best = v.x; int bi = 0;
-        if (v.y > best) { best = v.y; bi = 1; }
-        if (v.z > best) { best = v.z; bi = 2; }
-        if (v.w > best) { best = v.w; bi = 3; }
-        pv[al * pitch + pos - 1] = best;
-        pi[al * pitch + pos - 1] = (pos - 1) * 4 + bi;
+    // loads are issued 8 at a time into registers before anything is consumed (no load -> use -> load chain)
+    for (int base0 = 0; vec && base0 < na * n4; base0 += 8 * 32) {
+        float4 buf[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int idx = base0 + q * 32 + lane;
+            if (idx < na * n4) buf[q] = base[idx];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int idx = base0 + q * 32 + lane;
+            if (idx >= na * n4) continue;
+            const int al = idx / n4, pos = idx - al * n4;
+            if (pos == 0) continue;
+            const float4 v = buf[q];
+            float best = v.x; int bi = 0;
+            if (v.y > best) { best = v.y; bi = 1; }
+            if (v.z > best) { best = v.z; bi = 2; }
+            if (v.w > best) { best = v.w; bi = 3; }
+            pv[al * pitch + pos - 1] = best;
+            pi[al * pitch + pos - 1] = (pos - 1) * 4 + bi;
+        }
     }
     __syncwarp();
 

@@ -136,6 +136,35 @@ template <> struct SmemPix<float> {
     }
 };
 
+// packed bf16x2 helpers for the bf16 product path of K3: the 2x2 average is formed with three HADD2
+// (each rounds to bf16: two roundings more than an fp32 sum, <= 3 * 2^-9 relative) and one exact x0.25;
+// the 3x3 max is exact.  This quarters the instruction count of this issue-bound kernel; the fp32
+// validation path keeps torch's exact summation order.
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_quarter(uint32_t a) {
+    const __nv_bfloat162 q = __floats2bfloat162_rn(0.25f, 0.25f);
+    __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), q);
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 bf8_avg4(uint4 a, uint4 b, uint4 c, uint4 d) {
+    uint4 r;
+    r.x = bf2_quarter(bf2_add(bf2_add(bf2_add(a.x, b.x), c.x), d.x));
+    r.y = bf2_quarter(bf2_add(bf2_add(bf2_add(a.y, b.y), c.y), d.y));
+    r.z = bf2_quarter(bf2_add(bf2_add(bf2_add(a.z, b.z), c.z), d.z));
+    r.w = bf2_quarter(bf2_add(bf2_add(bf2_add(a.w, b.w), c.w), d.w));
+    return r;
+}
+__device__ __forceinline__ uint4 bf8_max(uint4 a, uint4 b) {
+    return make_uint4(bf2_max(a.x, b.x), bf2_max(a.y, b.y), bf2_max(a.z, b.z), bf2_max(a.w, b.w));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256, 3) adown_tiled_kernel(DView x, DView lo, DView hi, int half, int tiles_x, int tiles_y) {
     constexpr int CHN = SmemPix<T>::CHN, G = CHN / 8;
@@ -151,17 +180,78 @@ __global__ void __launch_bounds__(256, 3) adown_tiled_kernel(DView x, DView lo, 
     const int tid = threadIdx.x;
     const T* xp = reinterpret_cast<const T*>(x.ptr);
 
-    for (int i = tid; i < AD_ROWS * AD_COLS * 8; i += 256) {
+    // every thread issues ALL of its 16-byte loads into registers first, then stores them to shared memory
+    // (a load -> store -> load loop would serialise one HBM round trip per chunk)
+    constexpr int NLDS = (AD_ROWS * AD_COLS * 8 + 255) / 256;       // 11
+    uint4 buf[NLDS];
+#pragma unroll
+    for (int q = 0; q < NLDS; ++q) {
+        const int i = tid + 256 * q;
         const int v = i & 7, pix = i >> 3;
         const int r = pix / AD_COLS, c = pix - r * AD_COLS;
         const int iy = iy0 + r, ix = ix0 + c;
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (iy >= 0 && iy < x.H && ix >= 0 && ix < x.W)
-            u = *reinterpret_cast<const uint4*>(xp + dview_pix(x, b, iy, ix) + c0 + v * (16 / (int)sizeof(T)));
-        tile[r][c][v] = u;
+        buf[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (i < AD_ROWS * AD_COLS * 8 && iy >= 0 && iy < x.H && ix >= 0 && ix < x.W)
+            buf[q] = *reinterpret_cast<const uint4*>(xp + dview_pix(x, b, iy, ix) + c0 + v * (16 / (int)sizeof(T)));
+    }
+#pragma unroll
+    for (int q = 0; q < NLDS; ++q) {
+        const int i = tid + 256 * q;
+        if (i < AD_ROWS * AD_COLS * 8) {
+            const int v = i & 7, pix = i >> 3;
+            const int r = pix / AD_COLS, c = pix - r * AD_COLS;
+            tile[r][c][v] = buf[q];
+        }
     }
     __syncthreads();
 
+    if constexpr (sizeof(T) == 2) {
+        __nv_bfloat16* lop = reinterpret_cast<__nv_bfloat16*>(lo.ptr);
+        __nv_bfloat16* hip = reinterpret_cast<__nv_bfloat16*>(hi.ptr);
+        if (c0 < half) {
+            for (int i = tid; i < 2 * AD_TY * 2 * AD_TX * G; i += 256) {
+                const int g = i % G;
+                const int axl = (i / G) % (2 * AD_TX), ayl = i / (G * 2 * AD_TX);
+                const int ay = 2 * oy0 + ayl, ax = 2 * ox0 + axl;
+                const bool ok = ay < Ha && ax < Wa;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (ok) o = bf8_avg4(tile[ayl + 1][axl + 1][g], tile[ayl + 1][axl + 2][g], tile[ayl + 2][axl + 1][g], tile[ayl + 2][axl + 2][g]);
+                if (lo.layout == YRE_PHASE4) {
+                    if ((ay >> 1) < lo.Hp && (ax >> 1) < lo.Wp) *reinterpret_cast<uint4*>(lop + dview_pix(lo, b, ay, ax) + c0 + g * 8) = o;
+                } else if (ok) {
+                    *reinterpret_cast<uint4*>(lop + dview_pix(lo, b, ay, ax) + c0 + g * 8) = o;
+                }
+            }
+        } else {
+            for (int i = tid; i < AD_TY * AD_TX * G; i += 256) {
+                const int g = i % G;
+                const int oxl = (i / G) % AD_TX, oyl = i / (G * AD_TX);
+                const int oy = oy0 + oyl, ox = ox0 + oxl;
+                if (oy >= hi.H || ox >= hi.W) continue;
+                uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);      // -inf pairs
+                uint4 prev[4], cur[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) prev[q] = tile[2 * oyl][2 * oxl + q][g];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cur[q] = tile[2 * oyl + j + 1][2 * oxl + q][g];
+                    const int ay = 2 * oy - 1 + j;
+                    if (ay >= 0 && ay < Ha) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            const int ax = 2 * ox - 1 + q;
+                            if (ax >= 0 && ax < Wa) m = bf8_max(m, bf8_avg4(prev[q], prev[q + 1], cur[q], cur[q + 1]));
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) prev[q] = cur[q];
+                }
+                *reinterpret_cast<uint4*>(hip + dview_pix(hi, b, oy, ox) + (c0 - half) + g * 8) = m;
+            }
+        }
+        return;
+    }
     if (c0 < half) {
         // (2*TY) x (2*TX) average pixels x G channel groups; item -> (ayl, axl, g), g fastest
         for (int i = tid; i < 2 * AD_TY * 2 * AD_TX * G; i += 256) {

@@ -117,7 +117,7 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, cons
 // and the global loads of segment n+1 are issued into registers before segment n is computed, so
 // the HBM latency hides behind the MMA + store work of the current segment.
 template <int STRIDE>
-__global__ void __launch_bounds__(128, 4) stem_mma_kernel(const StemParams p, int segs, long long total_tiles) {
+__global__ void __launch_bounds__(128, 3) stem_mma_kernel(const StemParams p, int segs, long long total_tiles) {
     constexpr int NCOLS = SM_PX * STRIDE + 2;                    // input columns one segment needs
     constexpr int PITCH = NCOLS + 1;
     constexpr int NLD = (9 * NCOLS + 31) / 32;                   // loads per lane (Cin <= 3 -> 9 smem rows)
@@ -162,34 +162,42 @@ __global__ void __launch_bounds__(128, 4) stem_mma_kernel(const StemParams p, in
                 } else aoff[ks][h][e] = -1;
             }
 
-    const long long wstride = (long long)gridDim.x * 4;
-    long long tile = (long long)blockIdx.x * 4 + warp;
+    // segment cursor (seg, oy, b) advanced by the constant warp stride with carries: no div/mod in the loop
+    const int wstride = (int)gridDim.x * 4;
+    const int d_seg = wstride % segs, d_oy = (wstride / segs) % p.Ho, d_b = (wstride / segs) / p.Ho;
+    int tile = (int)blockIdx.x * 4 + warp;
+    int seg = tile % segs, oy = (tile / segs) % p.Ho, b = (tile / segs) / p.Ho;
+    const int ntiles = (int)total_tiles;
     float pre[NLD];
+    // per-lane constants of the gather: (row, col) of load q never change
+    int ld_off[NLD];              // ci * H * W + (dy - 1) * W + col - 1
+    int ld_dy[NLD], ld_col[NLD];
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+        const int i = lane + 32 * q;
+        const int row = i / NCOLS, col = i - row * NCOLS;
+        const int ci = row / 3, dy = row - 3 * ci;
+        ld_dy[q] = (row < nrows) ? dy - 1 : -100000;
+        ld_col[q] = col - 1;
+        ld_off[q] = ci * p.H * p.W + (dy - 1) * p.W + col - 1;
+    }
 
-    auto fetch = [&](long long tl) {                             // global -> registers for segment tl
-        const int seg = (int)(tl % segs);
-        const long long r = tl / segs;
-        const int oy = (int)(r % p.Ho), b = (int)(r / p.Ho);
-        const int ix0 = seg * SM_PX * STRIDE - 1;
+    auto fetch = [&](int fb, int foy, int fseg) {                // global -> registers for one segment
+        const int iy0 = foy * STRIDE, ix0 = fseg * SM_PX * STRIDE;
+        const float* base = p.x + ((long long)fb * p.Cin * p.H + iy0) * p.W + ix0;
 #pragma unroll
         for (int q = 0; q < NLD; ++q) {
-            const int i = lane + 32 * q;
-            const int row = i / NCOLS, col = i - row * NCOLS;
-            const int ci = row / 3, dy = row - 3 * ci;
-            const int iy = oy * STRIDE + dy - 1, ix = ix0 + col;
+            const int iy = iy0 + ld_dy[q], ix = ix0 + ld_col[q];
             float v = 0.f;
-            if (row < nrows && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                v = __ldg(p.x + (((long long)b * p.Cin + ci) * p.H + iy) * p.W + ix);
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(base + ld_off[q]);
             pre[q] = v;
         }
     };
 
-    if (tile < total_tiles) fetch(tile);
-    for (; tile < total_tiles; tile += wstride) {
-        const int seg = (int)(tile % segs);
-        const long long r = tile / segs;
-        const int oy = (int)(r % p.Ho), b = (int)(r / p.Ho);
+    if (tile < ntiles) fetch(b, oy, seg);
+    for (; tile < ntiles; tile += wstride) {
         const int ox0 = seg * SM_PX;
+        const int cb = b, coy = oy;
         __syncwarp();                                            // previous segment's smem readers are done
 #pragma unroll
         for (int q = 0; q < NLD; ++q) {
@@ -198,7 +206,11 @@ __global__ void __launch_bounds__(128, 4) stem_mma_kernel(const StemParams p, in
             if (i < 9 * NCOLS) sin[row * PITCH + col] = pre[q];
         }
         __syncwarp();
-        if (tile + wstride < total_tiles) fetch(tile + wstride); // in flight while this segment is computed
+        // advance the cursor and start the next segment's loads: in flight while this segment is computed
+        seg += d_seg; int cy = seg >= segs; seg -= cy ? segs : 0;
+        oy += d_oy + cy; cy = oy >= p.Ho; oy -= cy ? p.Ho : 0;
+        b += d_b + cy;
+        if (tile + wstride < ntiles) fetch(b, oy, seg);
 
         float acc[8][4];
 #pragma unroll
@@ -234,7 +246,7 @@ __global__ void __launch_bounds__(128, 4) stem_mma_kernel(const StemParams p, in
             const int ox = ox0 + px;
             if (ox < p.Wo) {
                 const uint4 v = *reinterpret_cast<const uint4*>(&sout[px][c16 * 8]);
-                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + dview_pix(p.y, b, oy, ox) + c16 * 8) = v;
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + dview_pix(p.y, cb, coy, ox) + c16 * 8) = v;
             }
         }
     }
