@@ -13,7 +13,7 @@ from yolo_b200 import _lib as L
 lib = L.lib()
 lib.yre_debug_read_trace.argtypes = [C.c_void_p, C.c_int]
 lib.yre_debug_read_trace.restype = C.c_int
-NAMES = {1: "P:empty-ok", 2: "P:tma-issued", 10: "M:tmem-free", 11: "M:full-ok", 12: "M:mma-issued", 20: "E:start", 21: "E:acc-ready", 22: "E:done"}
+NAMES = {1: "P:empty-ok", 2: "P:tma-issued", 10: "M:tmem-free", 11: "M:full-ok", 12: "M:mma-issued", 20: "E:start", 21: "E:acc-ready", 22: "E:done", 23: "e:ld", 24: "e:math", 25: "e:bufwait", 26: "e:stored"}
 
 
 def run(Bn, H, W, Cin, Cout, k):
@@ -56,5 +56,8 @@ def run(Bn, H, W, Cin, Cout, k):
         print(" role", role, " ".join(line))
 
 
-for shape in [(8, 160, 160, 32, 32, 3), (8, 160, 160, 64, 64, 1), (8, 80, 80, 128, 128, 3), (8, 80, 80, 256, 256, 3)]:
+shapes = [(8, 160, 160, 32, 32, 3), (8, 160, 160, 64, 64, 1), (8, 80, 80, 128, 128, 3), (8, 80, 80, 256, 256, 3)]
+if len(sys.argv) > 1 and sys.argv[1] == 'mem':
+    shapes = [(64, 80, 80, 128, 128, 1), (64, 160, 160, 64, 64, 1)]
+for shape in shapes:
     run(*shape)

@@ -445,6 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (have) {
                     uint32_t w[32];
                     tmem_ld_wait();
+                    if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 23);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) w[i] = v[i];
                     // prefetch this warp's next chunk while the current one is processed
@@ -453,9 +454,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (have) TMEM_LD32(taddr + (uint32_t)(cn * 32), v);
                     float f[32];
                     epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col);
+                    if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 24);
                     if (p.tma_store) {
                         if (lane == 0) bulk_wait_read<1>();      // the store that used this buffer two chunks ago has read it
                         __syncwarp();
+                        if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 25);
                         const uint32_t buf = stg + obuf * p.stage_out_bytes;
                         store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
                         fence_async_smem();
@@ -465,6 +468,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             bulk_commit();
                         }
                         obuf ^= 1u;
+                        if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 26);
                     } else if (valid) {
                         store_direct<32>(p, f, pix, n0 + col);
                     }

@@ -27,12 +27,19 @@ struct DecodeParams {
     float* y;
 };
 
-template <typename T>
+__device__ __forceinline__ float sigmoid_fast(float z) {      // ex2.approx + rcp.approx: ~3e-7 abs error
+    return __fdividef(1.0f, 1.0f + __expf(-z));
+}
+
+// NC > 0: class count known at compile time (80 = COCO, the common case) so every index is a constant
+// division; NC == 0: runtime class count.
+template <typename T, int NC>
 __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float sm[];
-    const int CH = 64 + p.nc;               // floats per raw row
+    const int nc = NC > 0 ? NC : p.nc;
+    const int CH = 64 + nc;                 // floats per raw row
     const int PITCH = CH + 4;               // keeps 16B alignment, skews banks
-    const int OC = 4 + p.nc;
+    const int OC = 4 + nc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* s_raw = sm + warp * (TILE * PITCH + TILE * OC);   // [TILE][PITCH]
     float* s_out = s_raw + TILE * PITCH;                      // [TILE][OC]
@@ -44,7 +51,7 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
     const int a0 = (int)(wt % tiles_per_img) * TILE;
     const int na = min(TILE, p.A - a0);
 
-    // ---- per-anchor source (lanes 0..TILE-1 own one anchor each; broadcast by shuffle) ----
+    // ---- per-anchor geometry (lanes 0..TILE-1 own one anchor each) ----
     long long my_src = 0; int my_lvl = 0; float my_ax = 0.f, my_ay = 0.f, my_st = 0.f;
     if (lane < na) {
         const int a = a0 + lane;
@@ -56,31 +63,40 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
         my_src = dview_pix(p.raw[l], b, py, px); my_lvl = l;
         my_ax = (float)px + 0.5f; my_ay = (float)py + 0.5f; my_st = p.stride[l];
     }
-    // ---- stage the raw rows: flat 16-byte chunks over the tile, every lane busy ----
     const int chunks = CH / 4;
-    // All loads of a lane are issued back to back into registers BEFORE the first shared-memory store: a
-    // load -> store -> load loop would serialise one HBM round trip per chunk (that alone made the first
-    // version of this kernel ~3x slower than its bandwidth bound).
-    constexpr int MAXQ = 16;                                  // covers TILE * chunks <= 512, i.e. nc <= 192
     const int total = na * chunks;
-    for (int base0 = 0; base0 < total; base0 += 32 * MAXQ) {
-        float4 buf[MAXQ];
+    // Fast path: the tile's anchors are consecutive pixels of ONE level whose view spans the whole buffer,
+    // so their raw rows form one contiguous run of na*CH floats.  All loads of a lane are issued into
+    // registers before the first shared-memory store (no load -> store -> load round-trip chain).
+    const int lvl0 = __shfl_sync(0xffffffffu, my_lvl, 0), lvl1 = __shfl_sync(0xffffffffu, my_lvl, na - 1);
+    const long long src0 = __shfl_sync(0xffffffffu, my_src, 0);
+    constexpr int MAXQ = 10;                                  // one pass for nc <= 96 (9 loads per lane at nc = 80)
+    if (lvl0 == lvl1 && p.raw[lvl0].C_total == CH) {
+        const void* basep = p.raw[lvl0].ptr;
+        for (int base0 = 0; base0 < total; base0 += 32 * MAXQ) {
+            float4 buf[MAXQ];
 #pragma unroll
-        for (int q = 0; q < MAXQ; ++q) {
-            const int i = base0 + q * 32 + lane;
+            for (int q = 0; q < MAXQ; ++q) {
+                const int i = base0 + q * 32 + lane;
+                if (i < total) buf[q] = ld4<T>(basep, src0 + (long long)i * 4);
+            }
+#pragma unroll
+            for (int q = 0; q < MAXQ; ++q) {
+                const int i = base0 + q * 32 + lane;
+                if (i < total) {
+                    const int al = i / chunks, ck = i - al * chunks;
+                    *reinterpret_cast<float4*>(s_raw + al * PITCH + ck * 4) = buf[q];
+                }
+            }
+        }
+    } else {
+        for (int base0 = 0; base0 < total; base0 += 32) {        // rare: tile straddles two levels / windowed view
+            const int i = base0 + lane;
             const bool act = i < total;
             const int al = act ? i / chunks : 0, ck = i - al * chunks;
             const long long src = __shfl_sync(0xffffffffu, my_src, al);
             const int lvl = __shfl_sync(0xffffffffu, my_lvl, al);
-            if (act) buf[q] = ld4<T>(p.raw[lvl].ptr, src + ck * 4);
-        }
-#pragma unroll
-        for (int q = 0; q < MAXQ; ++q) {
-            const int i = base0 + q * 32 + lane;
-            if (i < total) {
-                const int al = i / chunks, ck = i - al * chunks;
-                *reinterpret_cast<float4*>(s_raw + al * PITCH + ck * 4) = buf[q];
-            }
+            if (act) *reinterpret_cast<float4*>(s_raw + al * PITCH + ck * 4) = ld4<T>(p.raw[lvl].ptr, src + ck * 4);
         }
     }
     __syncwarp();
@@ -107,14 +123,14 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
                 den += ex;
                 num = fmaf(ex, p.dfl_w[k], num);
             }
-            e = num / den;
+            e = __fdividef(num, den);
         }
     }
     // ---- boxes: lane a (< TILE) gathers its four sides from lanes 4a..4a+3 ----
     {
-        const int src0 = (lane & 7) * 4;
-        const float e0 = __shfl_sync(0xffffffffu, e, src0), e1 = __shfl_sync(0xffffffffu, e, src0 + 1);
-        const float e2 = __shfl_sync(0xffffffffu, e, src0 + 2), e3 = __shfl_sync(0xffffffffu, e, src0 + 3);
+        const int s0 = (lane & 7) * 4;
+        const float e0 = __shfl_sync(0xffffffffu, e, s0), e1 = __shfl_sync(0xffffffffu, e, s0 + 1);
+        const float e2 = __shfl_sync(0xffffffffu, e, s0 + 2), e3 = __shfl_sync(0xffffffffu, e, s0 + 3);
         if (lane < na) {
             const float x1 = my_ax - e0, y1 = my_ay - e1, x2 = my_ax + e2, y2 = my_ay + e3;
             float* o = s_out + lane * OC;
@@ -124,10 +140,17 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
             o[3] = (y2 - y1) * my_st;
         }
     }
-    // ---- class scores: lanes stride the classes of each anchor (no div/mod) ----
-    for (int al = 0; al < na; ++al)
-        for (int c = lane; c < p.nc; c += 32)
-            s_out[al * OC + 4 + c] = __frcp_rn(1.0f + __expf(-s_raw[al * PITCH + 64 + c]));
+    // ---- class scores: float4 vectors, flat over (anchor, class/4) ----
+    {
+        const int nc4 = nc / 4;
+        for (int i = lane; i < na * nc4; i += 32) {
+            const int al = i / nc4, c4 = i - al * nc4;
+            const float4 z = *reinterpret_cast<const float4*>(s_raw + al * PITCH + 64 + c4 * 4);
+            float4 r;
+            r.x = sigmoid_fast(z.x); r.y = sigmoid_fast(z.y); r.z = sigmoid_fast(z.z); r.w = sigmoid_fast(z.w);
+            *reinterpret_cast<float4*>(s_out + al * OC + 4 + c4 * 4) = r;
+        }
+    }
     __syncwarp();
 
     // ---- contiguous coalesced store of na*OC floats ----
@@ -169,11 +192,17 @@ int launch_decode(const yre_decode_desc& d, cudaStream_t s) {
     dim3 grid((unsigned)((tiles + WARPS - 1) / WARPS));
     if (smem > 200 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "decode: nc=%d too large for the staging tile", d.nc);
     if (smem > 48 * 1024) {
-        YRE_CUDA(cudaFuncSetAttribute(decode_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        YRE_CUDA(cudaFuncSetAttribute(decode_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        YRE_CUDA(cudaFuncSetAttribute(decode_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        YRE_CUDA(cudaFuncSetAttribute(decode_kernel<__nv_bfloat16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if (d.raw[0].dtype == YRE_F32) decode_kernel<float><<<grid, WARPS * 32, smem, s>>>(p);
-    else decode_kernel<__nv_bfloat16><<<grid, WARPS * 32, smem, s>>>(p);
+    const bool f32 = d.raw[0].dtype == YRE_F32;
+    if (d.nc == 80) {
+        if (f32) decode_kernel<float, 80><<<grid, WARPS * 32, smem, s>>>(p);
+        else decode_kernel<__nv_bfloat16, 80><<<grid, WARPS * 32, smem, s>>>(p);
+    } else {
+        if (f32) decode_kernel<float, 0><<<grid, WARPS * 32, smem, s>>>(p);
+        else decode_kernel<__nv_bfloat16, 0><<<grid, WARPS * 32, smem, s>>>(p);
+    }
     YRE_LAUNCH_CHECK("dfl_decode_score");
     return YRE_OK;
 }
