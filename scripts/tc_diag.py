@@ -24,11 +24,25 @@ CASES = [
 ]
 
 
+BIG = [
+    (64, 80, 80, 256, 0, 256, 320, 3, 1, 1, 0, 0),    # bn=160 -> 3 accumulators
+    (64, 40, 40, 256, 0, 256, 256, 3, 1, 1, 0, 0),    # bn=256 -> 2 accumulators, single pipe
+    (64, 160, 160, 64, 0, 64, 64, 3, 1, 1, 1, 0),     # many tiles, residual, dual pipe
+    (64, 159, 159, 128, 0, 128, 128, 3, 2, 1, 0, 0),  # stride 2 from parity planes
+    (64, 160, 160, 32, 0, 32, 32, 3, 1, 1, 0, 0),     # BLOCK_K=32
+    (64, 40, 40, 1024, 0, 1024, 512, 1, 1, 1, 0, 0),  # 2 n-tiles of 256
+    (64, 80, 80, 256, 0, 256, 80, 1, 1, 0, 0, 1),     # fp32 direct-store head conv
+    (64, 160, 160, 64, 0, 32, 32, 3, 1, 1, 0, 0),     # channel window of a wider buffer, BLOCK_K=32
+    (16, 160, 160, 64, 0, 32, 32, 3, 1, 1, 0, 0),
+    (64, 160, 160, 64, 32, 32, 32, 3, 1, 1, 0, 0),
+]
+
+
 def run_case(i):
     import torch
     from yolo_b200 import _lib as L
     lib = L.lib()
-    Bn, H, W, Ct, coff, Cin, Cout, k, stride, act, res, of32 = CASES[i]
+    Bn, H, W, Ct, coff, Cin, Cout, k, stride, act, res, of32 = ALL[i]
     g = torch.Generator().manual_seed(i)
     dev = "cuda"
     if stride == 2:
@@ -66,7 +80,7 @@ def run_case(i):
     err = (a - b).abs()
     tol = 2e-2 * max(1.0, a.abs().max().item())
     bad = err > tol
-    print(f"case {i} {CASES[i]}: max|ffma|={a.abs().max():.3f} max err={err.max():.4f} bad={bad.float().mean():.4f} "
+    print(f"case {i} {ALL[i]}: max|ffma|={a.abs().max():.3f} max err={err.max():.4f} bad={bad.float().mean():.4f} "
           f"untouched(7.0)={(b == 7.0).float().mean():.4f}")
     if bad.any():
         idx = bad.nonzero()
@@ -79,11 +93,13 @@ def run_case(i):
     return 0
 
 
+ALL = CASES + BIG
+
 if __name__ == "__main__":
     arg = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if arg == "all":
+    if arg in ("all", "big"):
         rcs = []
-        for i in range(len(CASES)):
+        for i in (range(len(CASES)) if arg == "all" else range(len(CASES), len(ALL))):
             try:
                 r = subprocess.run([sys.executable, __file__, str(i)], timeout=120, capture_output=True, text=True)
                 print(r.stdout.strip() or f"case {i}: no output", flush=True)

@@ -18,8 +18,11 @@
 //
 // Warp roles (256 threads, 1 CTA / SM, persistent over a static tile schedule):
 //   warp 0 : TMA producer          warp 1 : tcgen05.mma issuer       warp 2 : TMEM alloc / dealloc
-//   warps 4..11 : epilogue; warp w owns TMEM lane quarter w%4 (32 pixels) and every other 32-column
-//   chunk, with its own double-buffered staging tile and its own TMA stores -- no CTA-wide barrier
+//   warps 4..15 : epilogue, three groups of four warps; a group takes every third tile of the CTA (its
+//   accumulator sits in one of up to 4 TMEM buffers), warp w owns TMEM lane quarter w%4 (32 pixels), with its
+//   own double-buffered staging tile and its own TMA stores -- no CTA-wide barrier.  The epilogue is
+//   MUFU-bound (one tanh per output, 16 MUFU lanes per SM), so three warps per scheduler keep that pipe
+//   busy while their siblings wait on TMEM loads / staging / stores.
 // Epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> 128B-swizzled shared-memory staging
 // tile -> TMA store (cp.async.bulk.tensor) into the consumer's channel window (concat-slice write,
 // ragged tile edges clipped by the TMA unit).  fp32 outputs (the raw head logits) use direct 16-byte
@@ -35,10 +38,11 @@ struct ConvTcPlan;
 
 namespace {
 
-constexpr int NUM_THREADS = 384;    // 12 warps: TMA, MMA, TMEM-alloc, spare, 8 epilogue
+// threads per CTA: 4 role warps (2 x (TMA, MMA)) + 2 or 3 epilogue warpgroups (4 TMEM lane quarters each).
+// 384 threads leave 168 registers per thread, 512 only 128: the third warpgroup pays off for small-N tiles only.
+constexpr int NT_2WG = 384, NT_3WG = 512;
 constexpr int BLOCK_M = 128;
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;     // columns between the two accumulator buffers
 
 struct TcParams {
     int tw, th, tb;                 // tile patch; tw*th*tb == 128
@@ -58,6 +62,9 @@ struct TcParams {
     int* dbg;                       // optional watchdog record (may be null)
     int tma_store;                  // 1: bf16 output through the smem-staged TMA store
     int npipes;                     // 1 or 2 (producer, MMA) warp pairs
+    int nthreads;                   // NT_2WG or NT_3WG
+    int nacc, acc_stride;           // TMEM accumulator ring (2..6 buffers), columns per buffer
+    int ngroups, tgroups, csplit;   // epilogue warpgroups = tgroups (tiles round-robin) x csplit (32-col chunks round-robin)
     int stw, sth, stb;              // the 32 pixels of one TMEM lane quarter as a (stb x sth x stw) sub-patch
     uint32_t stage_out_bytes;       // bytes of one per-warp staging buffer (32 rows x 32 ch x 2 = 2048)
 };
@@ -293,8 +300,8 @@ __device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base
     }
 }
 
-template <int KSTEPS>     // BLOCK_K / 16: 4 (128-byte swizzle) or 2 (64-byte swizzle)
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int KSTEPS, int NT>     // KSTEPS = BLOCK_K / 16: 4 (128-byte swizzle) or 2 (64-byte swizzle); NT = threads per CTA
+__global__ void __launch_bounds__(NT, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -303,19 +310,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
     const uint32_t S = (uint32_t)p.stages;
     const uint32_t out_base = sbase + S * stage_bytes;       // 8 warps x 2 staging buffers for the TMA-store epilogue
-    const uint32_t bar_base = out_base + 16u * p.stage_out_bytes;
-    // barrier i at bar_base + 8*i : full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4)
-    const uint32_t tmem_slot = bar_base + 8u * (2u * S + 4u);
+    const uint32_t bar_base = out_base + 8u * (uint32_t)p.ngroups * p.stage_out_bytes;   // staging: 4 warps x 2 buffers per group
+    // barrier i at bar_base + 8*i : full[0..S), empty[S..2S), tmem_full[2S..2S+8), tmem_empty[2S+8..2S+16)
+    const uint32_t tmem_slot = bar_base + 8u * (2u * S + 16u);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
     float* sbias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - raw));     // [Cout] bias copy (zeros if none)
-    for (int i = threadIdx.x; i < p.Cout; i += NUM_THREADS) sbias[i] = p.bias ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < p.Cout; i += NT) sbias[i] = p.bias ? p.bias[i] : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); if (p.tma_store) tma_prefetch_desc(&tmY); }
     if (warp == 1 && lane == 0) {
         for (uint32_t i = 0; i < S; ++i) { mbar_init(bar_base + 8u * i, 1); mbar_init(bar_base + 8u * (S + i), 1); }
-        for (uint32_t i = 0; i < 2; ++i) { mbar_init(bar_base + 8u * (2u * S + i), 1); mbar_init(bar_base + 8u * (2u * S + 2u + i), 8); }
+        for (uint32_t i = 0; i < 8; ++i) { mbar_init(bar_base + 8u * (2u * S + i), 1); mbar_init(bar_base + 8u * (2u * S + 8u + i), 4u * (uint32_t)p.csplit); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -381,11 +388,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t stage16 = stage_bytes >> 4, a16 = p.a_bytes >> 4;
         const uint32_t ring_lo = desc_lo0 + ((sbase + pipe * S2 * stage_bytes) >> 4);   // smem < 256 KB: no overflow of the 14-bit field
         int tn = 0;
-        uint32_t j = pipe;                               // local tile counter: accumulator j&1, phase (j>>1)&1
-        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += (int)(NP * gridDim.x), j += NP) {
-            const uint32_t acc = j & 1u, acc_phase = (j >> 1) & 1u;
-            const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 2u + acc);
-            const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+        // local tile j of this CTA uses accumulator j % nacc, in phase (j / nacc) & 1
+        const uint32_t NACC = (uint32_t)p.nacc;
+        uint32_t acc = pipe % NACC, acc_phase = (pipe / NACC) & 1u;
+        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += (int)(NP * gridDim.x)) {
+            const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 8u + acc);
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
             mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
             tc_fence_after();
             if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 10);
@@ -408,11 +416,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 12);
                 if (++stage == S2) { stage = 0; phase ^= 1u; }
             }
+            acc += NP;
+            while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
-    } else if (warp >= 4) {
-        // ================= epilogue (8 warps, warp-local: no CTA barrier) =================
+    } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
+        // ================= epilogue (warp-local, no CTA barrier) =================
+        // warpgroup grp = (tg, cs): tile-group tg takes local tiles tg, tg+GT, ...; inside a tile the csplit
+        // warpgroups of a tile-group share the 32-column chunks round-robin (cs, cs+CS, ...).
         const int q = warp & 3;                 // TMEM lane quarter -> rows 32q .. 32q+31 of the tile
-        const int hsel = (warp - 4) >> 2;       // takes the 32-column chunks c with (c & 1) == hsel
+        const int grp = (warp - 4) >> 2;
+        const uint32_t G = (uint32_t)p.tgroups, NACC = (uint32_t)p.nacc;
+        const int tg = grp % p.tgroups, cs = grp / p.tgroups, CS = p.csplit;
         const int row = q * 32 + lane;
         const int patch = p.tw * p.th;
         const int bi = row / patch, rem = row % patch, yy = rem / p.tw, xx = rem % p.tw;
@@ -421,44 +435,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t stg = out_base + (uint32_t)(warp - 4) * 2u * p.stage_out_bytes;
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);         // SWIZZLE_64B pattern of this row
         const int nchunks = (p.block_n + 31) >> 5;
-        uint32_t acc = 0, acc_phase = 0, obuf = 0;
+        const bool tracer = (warp == 4 && lane == 0);
+        uint32_t acc = (uint32_t)tg % NACC, acc_phase = ((uint32_t)tg / NACC) & 1u, obuf = 0;
         int tn = 0;
         TileCur tc;
-        tc.init(p, blockIdx.x, (int)gridDim.x);
-        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, tc.step(p)) {
+        tc.init(p, blockIdx.x + tg * (int)gridDim.x, (int)(G * gridDim.x));
+        for (int t = blockIdx.x + tg * (int)gridDim.x; t < p.num_tiles; t += (int)(G * gridDim.x), tc.step(p)) {
             const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt * p.tb, n0 = tc.nt * p.block_n;
             const int x = x0 + xx, y = y0 + yy, b = b0 + bi;
             const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
             const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
-            const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 2u + acc);
-            if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 20);
+            const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 8u + acc);
+            if (tracer) trace(p.dbg, 2, tn, 20);
             mbar_wait(tfull, acc_phase, p.dbg, 4);
             tc_fence_after();
-            if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 21);
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_STRIDE;
+            if (tracer) trace(p.dbg, 2, tn, 21);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
             uint32_t v[32];
-            int c = hsel;
-            bool have = false;
-            if (c < nchunks && c * 32 + 32 <= p.block_n) { TMEM_LD32(taddr + (uint32_t)(c * 32), v); have = true; }
-            for (; c < nchunks; c += 2) {
+            bool have = (cs * 32 + 32 <= p.block_n);
+            if (have) TMEM_LD32(taddr + (uint32_t)(cs * 32), v);
+            for (int c = cs; c < nchunks; c += CS) {
                 const int col = c * 32;
                 if (have) {
                     uint32_t w[32];
                     tmem_ld_wait();
-                    if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 23);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) w[i] = v[i];
-                    // prefetch this warp's next chunk while the current one is processed
-                    const int cn = c + 2;
-                    have = (cn < nchunks && cn * 32 + 32 <= p.block_n);
-                    if (have) TMEM_LD32(taddr + (uint32_t)(cn * 32), v);
+                    // prefetch this group's next chunk of the accumulator while the current one is processed
+                    have = ((c + CS) < nchunks && (c + CS) * 32 + 32 <= p.block_n);
+                    if (have) TMEM_LD32(taddr + (uint32_t)(col + 32 * CS), v);
+                    if (tracer) trace(p.dbg, 2, tn, 23);
                     float f[32];
                     epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col);
-                    if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 24);
+                    if (tracer) trace(p.dbg, 2, tn, 24);
                     if (p.tma_store) {
                         if (lane == 0) bulk_wait_read<1>();      // the store that used this buffer two chunks ago has read it
                         __syncwarp();
-                        if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 25);
                         const uint32_t buf = stg + obuf * p.stage_out_bytes;
                         store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
                         fence_async_smem();
@@ -468,7 +480,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             bulk_commit();
                         }
                         obuf ^= 1u;
-                        if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 26);
+                        if (tracer) trace(p.dbg, 2, tn, 26);
                     } else if (valid) {
                         store_direct<32>(p, f, pix, n0 + col);
                     }
@@ -485,8 +497,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty);
-            if (warp == 4 && lane == 0) trace(p.dbg, 2, tn, 22);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (tracer) trace(p.dbg, 2, tn, 22);
+            acc += G;
+            while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
         if (p.tma_store && lane == 0) bulk_wait_all();           // stores must land before the CTA retires
     }
@@ -606,20 +619,37 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     p.stw = p.tw < 32 ? p.tw : 32;
     p.sth = (32 / p.stw) < p.th ? (32 / p.stw) : p.th;
     p.stb = 32 / (p.stw * p.sth);
+    // TMEM accumulator ring (nacc buffers of acc_stride columns), epilogue groups and (producer, MMA) pairs.
+    // Tile j of a CTA uses accumulator j % nacc, epilogue group j % ngroups and pair j % npipes.  Every
+    // mbarrier is waited on by parity, so a buffer must always be served by the SAME group and the SAME pair
+    // (otherwise a waiter can fall two phases behind and the parity aliases): nacc % ngroups == 0 and
+    // nacc % npipes == 0.
+    // With one buffer per tile-group the group idles while its buffer is refilled, so keep nacc >= 2 * tgroups;
+    // where TMEM only holds 2-3 buffers, split the chunks of each tile over the warpgroups instead.
+    p.nthreads = bn <= 64 ? NT_3WG : NT_2WG;
+    { const int f = env_int("YRE_TC_THREADS", 0); if (f == NT_2WG || f == NT_3WG) p.nthreads = f; }
+    const int maxg = (p.nthreads / 32 - 4) / 4;
+    if (bn <= 64)       { p.acc_stride = 64;  p.nacc = 6; p.tgroups = maxg; p.csplit = 1; }
+    else if (bn <= 128) { p.acc_stride = 128; p.nacc = 4; p.tgroups = 2; p.csplit = 1; }
+    else if (bn <= 160) { p.acc_stride = 160; p.nacc = 3; p.tgroups = 1; p.csplit = maxg; }
+    else                { p.acc_stride = 256; p.nacc = 2; p.tgroups = 1; p.csplit = maxg; }
+    { const int f = env_int("YRE_TC_TGROUPS", 0); if (f >= 1 && f <= maxg && p.nacc % f == 0) { p.tgroups = f; if (p.tgroups * p.csplit > maxg) p.csplit = 1; } }
+    { const int f = env_int("YRE_TC_SPLIT", 0); if (f >= 1 && f * p.tgroups <= maxg) p.csplit = f; }
+    while (p.csplit > 1 && p.csplit > (bn + 31) / 32) --p.csplit;   // every warpgroup owns at least one chunk
+    p.ngroups = p.tgroups * p.csplit;
+    const uint32_t n_stage_bufs = 8u * (uint32_t)p.ngroups;         // 4 warps x 2 buffers per group
     const uint32_t smem_cap = 227u * 1024u - 1024u - 256u - (uint32_t)Cout * 4u;   // alignment slack + barriers + bias copy
-    int stages = (int)((smem_cap - 16u * p.stage_out_bytes) / stage_bytes);
+    int stages = (int)((smem_cap - n_stage_bufs * p.stage_out_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
     const int force_st = env_int("YRE_TC_STAGES", 0);
     if (force_st >= 2 && force_st <= stages) stages = force_st;
     if (stages < 2) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: tile does not fit shared memory"); }
-    // two (producer, MMA) pairs when the ring is deep enough to give each at least 3 stages; big-stage
-    // (compute-bound) tiles keep one pair with the whole ring, which hides the TMA latency better
-    p.npipes = stages >= 6 ? 2 : 1;
-    const int force_np = env_int("YRE_TC_PIPES", 0);
-    if (force_np == 1 || (force_np == 2 && stages >= 4)) p.npipes = force_np;
+    // two (producer, MMA) pairs when the ring gives each at least 3 stages
+    p.npipes = (stages >= 6 && p.nacc % 2 == 0) ? 2 : 1;
+    { const int f = env_int("YRE_TC_PIPES", 0); if (f >= 1 && f <= 2 && p.nacc % f == 0 && stages >= 2 * f) p.npipes = f; }
     if (p.npipes == 2) stages &= ~1;
     p.stages = stages;
-    pl->smem = (size_t)stages * stage_bytes + 16 * p.stage_out_bytes + 8 * (2 * stages + 4) + 32 + (size_t)Cout * 4 + 1024;
+    pl->smem = (size_t)stages * stage_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 16) + 32 + (size_t)Cout * 4 + 1024;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     p.bias = d.bias; p.act = d.act;
     p.y = d.y.ptr; p.y_f32 = d.y.dtype == YRE_F32; p.y_ctot = d.y.C_total; p.y_coff = d.y.c_off;
@@ -683,12 +713,20 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4, NT_2WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, NT_2WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4, NT_3WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, NT_3WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    if (pl->p.block_k == 64) conv_tc_kernel<4><<<pl->grid, NUM_THREADS, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
-    else conv_tc_kernel<2><<<pl->grid, NUM_THREADS, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+    const bool k64 = pl->p.block_k == 64;
+    if (pl->p.nthreads == NT_3WG) {
+        if (k64) conv_tc_kernel<4, NT_3WG><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+        else     conv_tc_kernel<2, NT_3WG><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+    } else {
+        if (k64) conv_tc_kernel<4, NT_2WG><<<pl->grid, NT_2WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+        else     conv_tc_kernel<2, NT_2WG><<<pl->grid, NT_2WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+    }
     YRE_LAUNCH_CHECK("conv_tc");
     return YRE_OK;
 }
