@@ -35,6 +35,18 @@ def run(Bn, H, W, Cin, Cout, k):
     buf = (C.c_int * 8192)()
     lib.yre_debug_read_trace(buf, 8192)
     print(f"\n=== conv{k}x{k} {Cin}->{Cout} @{H}x{W} B{Bn}: {e0.elapsed_time(e1) * 1e3:.1f} us")
+    import struct
+    ent = []
+    for b in range(148):
+        o = 2048 + b * 8
+        g0 = ((buf[o + 1] & 0xffffffff) << 32) | (buf[o] & 0xffffffff); c0 = ((buf[o + 3] & 0xffffffff) << 32) | (buf[o + 2] & 0xffffffff)
+        g1 = ((buf[o + 5] & 0xffffffff) << 32) | (buf[o + 4] & 0xffffffff); c1 = ((buf[o + 7] & 0xffffffff) << 32) | (buf[o + 6] & 0xffffffff)
+        if g0 and g1: ent.append((g0, g1, c1 - c0))
+    if ent:
+        gmin = min(e[0] for e in ent); gmax = max(e[1] for e in ent)
+        durs = sorted(e[1] - e[0] for e in ent)
+        print(f" CTAs={len(ent)} grid span={gmax - gmin} ns; entry spread={max(e[0] for e in ent) - gmin} ns; CTA dur min/med/max={durs[0]}/{durs[len(durs)//2]}/{durs[-1]} ns;"
+              f" clk/ns med={sorted(e[2] / max(1, e[1] - e[0]) for e in ent)[len(ent)//2]:.3f}")
     evs = []
     for role in range(3):
         for n in range(96):

@@ -58,6 +58,9 @@ CONVS = [
     ((512, 256, 1, 1), {}, (3, 512, 13, 13)),                  # ragged: 13x13, batch 3
     ((1024, 512, 1, 1), {}, (1, 1024, 20, 20)),
     ((256, 80, 1, 1), {}, (1, 256, 16, 16)),                   # N = 80
+    ((64, 64, 3, 1), {}, (3, 64, 37, 29)),                     # halo kernel (8x16 patches), ragged in x and y
+    ((32, 32, 3, 1), {}, (2, 32, 50, 19)),                     # halo kernel, SWIZZLE_64B, one partial patch row
+    ((64, 32, 3, 1), {}, (1, 64, 48, 40)),                     # halo kernel, Cout != Cin
 ]
 
 

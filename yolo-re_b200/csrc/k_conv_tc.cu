@@ -67,6 +67,9 @@ struct TcParams {
     int ngroups, tgroups, csplit;   // epilogue warpgroups = tgroups (tiles round-robin) x csplit (32-col chunks round-robin)
     int stw, sth, stb;              // the 32 pixels of one TMEM lane quarter as a (stb x sth x stw) sub-patch
     uint32_t stage_out_bytes;       // bytes of one per-warp staging buffer (32 rows x 32 ch x 2 = 2048)
+    // weight-stationary halo variant (conv3_halo_kernel)
+    int halo;                       // 1: 3x3 stride-1 conv through the halo kernel
+    uint32_t halo_tx;               // bytes one halo box delivers (10 x 18 pixels x BLOCK_K channels)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -154,6 +157,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32
         "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same with separate high words for A and B (different stride-byte-offsets)
+__device__ __forceinline__ void umma_bf16_ab(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -300,11 +311,106 @@ __device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base
     }
 }
 
+// Epilogue role of one warp (warps 4..): tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 staging -> TMA store.
+// warpgroup grp = (tg, cs): tile-group tg takes local tiles tg, tg+GT, ...; inside a tile the csplit warpgroups of
+// a tile-group share the 32-column chunks round-robin.  tfull0 / tempty0 = addresses of the first accumulator
+// full / empty mbarrier (8 bytes apart per buffer).
+__device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* tmY, const float* sbias, int warp, int lane,
+                                              uint32_t tmem_base, uint32_t out_base, uint32_t tfull0, uint32_t tempty0) {
+        // ================= epilogue (warp-local, no CTA barrier) =================
+        // warpgroup grp = (tg, cs): tile-group tg takes local tiles tg, tg+GT, ...; inside a tile the csplit
+        // warpgroups of a tile-group share the 32-column chunks round-robin (cs, cs+CS, ...).
+        const int q = warp & 3;                 // TMEM lane quarter -> rows 32q .. 32q+31 of the tile
+        const int grp = (warp - 4) >> 2;
+        const uint32_t G = (uint32_t)p.tgroups, NACC = (uint32_t)p.nacc;
+        const int tg = grp % p.tgroups, cs = grp / p.tgroups, CS = p.csplit;
+        const int row = q * 32 + lane;
+        const int patch = p.tw * p.th;
+        const int bi = row / patch, rem = row % patch, yy = rem / p.tw, xx = rem % p.tw;
+        // origin of this warp's 32-pixel sub-patch inside the tile (row 32q)
+        const int r0 = q * 32, sb0 = r0 / patch, sy0 = (r0 % patch) / p.tw, sx0 = (r0 % patch) % p.tw;
+        const uint32_t stg = out_base + (uint32_t)(warp - 4) * 2u * p.stage_out_bytes;
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);         // SWIZZLE_64B pattern of this row
+        const int nchunks = (p.block_n + 31) >> 5;
+        const bool tracer = (warp == 4 && lane == 0);
+        uint32_t acc = (uint32_t)tg % NACC, acc_phase = ((uint32_t)tg / NACC) & 1u, obuf = 0;
+        int tn = 0;
+        TileCur tc;
+        tc.init(p, blockIdx.x + tg * (int)gridDim.x, (int)(G * gridDim.x));
+        for (int t = blockIdx.x + tg * (int)gridDim.x; t < p.num_tiles; t += (int)(G * gridDim.x), tc.step(p)) {
+            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt * p.tb, n0 = tc.nt * p.block_n;
+            const int x = x0 + xx, y = y0 + yy, b = b0 + bi;
+            const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+            const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
+            const uint32_t tfull = tfull0 + 8u * acc, tempty = tempty0 + 8u * acc;
+            if (tracer) trace(p.dbg, 2, tn, 20);
+            mbar_wait(tfull, acc_phase, p.dbg, 4);
+            tc_fence_after();
+            if (tracer) trace(p.dbg, 2, tn, 21);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
+            uint32_t v[32];
+            bool have = (cs * 32 + 32 <= p.block_n);
+            if (have) TMEM_LD32(taddr + (uint32_t)(cs * 32), v);
+            for (int c = cs; c < nchunks; c += CS) {
+                const int col = c * 32;
+                if (have) {
+                    uint32_t w[32];
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) w[i] = v[i];
+                    // prefetch this group's next chunk of the accumulator while the current one is processed
+                    have = ((c + CS) < nchunks && (c + CS) * 32 + 32 <= p.block_n);
+                    if (have) TMEM_LD32(taddr + (uint32_t)(col + 32 * CS), v);
+                    if (tracer) trace(p.dbg, 2, tn, 23);
+                    float f[32];
+                    epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col);
+                    if (tracer) trace(p.dbg, 2, tn, 24);
+                    if (p.tma_store) {
+                        if (lane == 0) bulk_wait_read<1>();      // the store that used this buffer two chunks ago has read it
+                        __syncwarp();
+                        const uint32_t buf = stg + obuf * p.stage_out_bytes;
+                        store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(tmY, buf, p.y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
+                            bulk_commit();
+                        }
+                        obuf ^= 1u;
+                        if (tracer) trace(p.dbg, 2, tn, 26);
+                    } else if (valid) {
+                        store_direct<32>(p, f, pix, n0 + col);
+                    }
+                } else {                         // 16-column tail (block_n % 32 == 16, direct-store outputs only)
+                    uint32_t w16[16];
+                    float f[16];
+                    TMEM_LD16(taddr + (uint32_t)col, w16);
+                    tmem_ld_wait();
+                    epilogue_math<16>(p, sbias, w16, f, valid, pix, n0 + col);
+                    if (valid) store_direct<16>(p, f, pix, n0 + col);
+                }
+            }
+            // every tcgen05.ld of this accumulator has completed: hand the TMEM buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+            if (tracer) trace(p.dbg, 2, tn, 22);
+            acc += G;
+            while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
+        }
+        if (p.tma_store && lane == 0) bulk_wait_all();           // stores must land before the CTA retires
+    }
+
 template <int KSTEPS, int NT>     // KSTEPS = BLOCK_K / 16: 4 (128-byte swizzle) or 2 (64-byte swizzle); NT = threads per CTA
 __global__ void __launch_bounds__(NT, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
+    if (p.dbg && threadIdx.x == 0) {       // trace mode: per-CTA entry stamp (globaltimer ns, SM clock)
+        const unsigned long long g = gtimer(); const long long c = clock64();
+        int* e = p.dbg + 2048 + blockIdx.x * 8;
+        e[0] = (int)(g & 0xffffffffull); e[1] = (int)(g >> 32); e[2] = (int)(c & 0xffffffffll); e[3] = (int)(c >> 32);
+    }
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
@@ -420,88 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
-        // ================= epilogue (warp-local, no CTA barrier) =================
-        // warpgroup grp = (tg, cs): tile-group tg takes local tiles tg, tg+GT, ...; inside a tile the csplit
-        // warpgroups of a tile-group share the 32-column chunks round-robin (cs, cs+CS, ...).
-        const int q = warp & 3;                 // TMEM lane quarter -> rows 32q .. 32q+31 of the tile
-        const int grp = (warp - 4) >> 2;
-        const uint32_t G = (uint32_t)p.tgroups, NACC = (uint32_t)p.nacc;
-        const int tg = grp % p.tgroups, cs = grp / p.tgroups, CS = p.csplit;
-        const int row = q * 32 + lane;
-        const int patch = p.tw * p.th;
-        const int bi = row / patch, rem = row % patch, yy = rem / p.tw, xx = rem % p.tw;
-        // origin of this warp's 32-pixel sub-patch inside the tile (row 32q)
-        const int r0 = q * 32, sb0 = r0 / patch, sy0 = (r0 % patch) / p.tw, sx0 = (r0 % patch) % p.tw;
-        const uint32_t stg = out_base + (uint32_t)(warp - 4) * 2u * p.stage_out_bytes;
-        const uint32_t sw = (uint32_t)((lane >> 1) & 3);         // SWIZZLE_64B pattern of this row
-        const int nchunks = (p.block_n + 31) >> 5;
-        const bool tracer = (warp == 4 && lane == 0);
-        uint32_t acc = (uint32_t)tg % NACC, acc_phase = ((uint32_t)tg / NACC) & 1u, obuf = 0;
-        int tn = 0;
-        TileCur tc;
-        tc.init(p, blockIdx.x + tg * (int)gridDim.x, (int)(G * gridDim.x));
-        for (int t = blockIdx.x + tg * (int)gridDim.x; t < p.num_tiles; t += (int)(G * gridDim.x), tc.step(p)) {
-            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt * p.tb, n0 = tc.nt * p.block_n;
-            const int x = x0 + xx, y = y0 + yy, b = b0 + bi;
-            const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
-            const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
-            const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 8u + acc);
-            if (tracer) trace(p.dbg, 2, tn, 20);
-            mbar_wait(tfull, acc_phase, p.dbg, 4);
-            tc_fence_after();
-            if (tracer) trace(p.dbg, 2, tn, 21);
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
-            uint32_t v[32];
-            bool have = (cs * 32 + 32 <= p.block_n);
-            if (have) TMEM_LD32(taddr + (uint32_t)(cs * 32), v);
-            for (int c = cs; c < nchunks; c += CS) {
-                const int col = c * 32;
-                if (have) {
-                    uint32_t w[32];
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) w[i] = v[i];
-                    // prefetch this group's next chunk of the accumulator while the current one is processed
-                    have = ((c + CS) < nchunks && (c + CS) * 32 + 32 <= p.block_n);
-                    if (have) TMEM_LD32(taddr + (uint32_t)(col + 32 * CS), v);
-                    if (tracer) trace(p.dbg, 2, tn, 23);
-                    float f[32];
-                    epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col);
-                    if (tracer) trace(p.dbg, 2, tn, 24);
-                    if (p.tma_store) {
-                        if (lane == 0) bulk_wait_read<1>();      // the store that used this buffer two chunks ago has read it
-                        __syncwarp();
-                        const uint32_t buf = stg + obuf * p.stage_out_bytes;
-                        store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_4d(&tmY, buf, p.y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
-                            bulk_commit();
-                        }
-                        obuf ^= 1u;
-                        if (tracer) trace(p.dbg, 2, tn, 26);
-                    } else if (valid) {
-                        store_direct<32>(p, f, pix, n0 + col);
-                    }
-                } else {                         // 16-column tail (block_n % 32 == 16, direct-store outputs only)
-                    uint32_t w16[16];
-                    float f[16];
-                    TMEM_LD16(taddr + (uint32_t)col, w16);
-                    tmem_ld_wait();
-                    epilogue_math<16>(p, sbias, w16, f, valid, pix, n0 + col);
-                    if (valid) store_direct<16>(p, f, pix, n0 + col);
-                }
-            }
-            // every tcgen05.ld of this accumulator has completed: hand the TMEM buffer back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty);
-            if (tracer) trace(p.dbg, 2, tn, 22);
-            acc += G;
-            while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
-        }
-        if (p.tma_store && lane == 0) bulk_wait_all();           // stores must land before the CTA retires
+        epilogue_role(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
     }
 
     tc_fence_before();
@@ -509,6 +534,154 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+    if (p.dbg && threadIdx.x == 0) {
+        const unsigned long long g = gtimer(); const long long c = clock64();
+        int* e = p.dbg + 2048 + blockIdx.x * 8;
+        e[4] = (int)(g & 0xffffffffull); e[5] = (int)(g >> 32); e[6] = (int)(c & 0xffffffffll); e[7] = (int)(c >> 32);
+    }
+}
+
+
+// ---- weight-stationary halo variant for small-channel 3x3 stride-1 convs -----------------------------------
+// The generic kernel re-reads every input pixel nine times (one shifted box per filter tap) and synchronises
+// once per tap; with Cin = Cout <= 64 a tap is only 32-128 tensor-pipe cycles of work, so those layers were
+// bound by the per-k-iteration handshake and by L2->SM traffic.  Here
+//   * the whole weight matrix (9 taps x Cout x Cin, <= 72 KB) is loaded ONCE per CTA and stays in shared memory;
+//   * a tile is an 8 (x) by 16 (y) pixel patch of one image, and ONE TMA box of 10 x 18 pixels (the patch plus
+//     its halo; out-of-bounds rows/columns zero-filled = the conv padding) is loaded per tile;
+//   * tap (ky,kx) is the same shared-memory tile read through a UMMA descriptor whose start address is moved by
+//     (ky*10 + kx) pixel rows and whose stride between 8-row groups is one halo row (10 pixels): the 8 rows of
+//     a group are the 8 consecutive pixels of one patch row, so no data is moved or duplicated.  The swizzle
+//     XOR is a function of the absolute shared-memory address on both the TMA write and the UMMA read side,
+//     so a start address that is not aligned to the 1024-byte swizzle repeat needs no descriptor base offset
+//     (measured: base_offset = 0 is bit-correct, a non-zero one is not);
+//   * the 9 x KSTEPS MMAs of a tile are issued back to back behind a single mbarrier wait.
+//   * one thread needs ~50 cycles per tcgen05.mma (descriptor moves on the uniform datapath), more than the
+//     16-32 cycles such a small MMA occupies the tensor pipe, so TWO warps issue, each taking every other
+//     tile; Cout is a template parameter so that every descriptor offset is an immediate.
+// Warp roles: warp 0 TMA producer, warps 1 and 3 MMA issuers, warp 2 TMEM alloc, warps 4.. epilogue.
+template <int KSTEPS, int COUT>
+__global__ void __launch_bounds__(NT_3WG, 1)
+conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmY, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    if (p.dbg && threadIdx.x == 0) {       // trace mode: per-CTA entry stamp (globaltimer ns, SM clock)
+        const unsigned long long g = gtimer(); const long long c = clock64();
+        int* e = p.dbg + 2048 + blockIdx.x * 8;
+        e[0] = (int)(g & 0xffffffffull); e[1] = (int)(g >> 32); e[2] = (int)(c & 0xffffffffll); e[3] = (int)(c >> 32);
+    }
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    constexpr uint32_t ROW_BYTES = KSTEPS * 32;               // one pixel row: BLOCK_K bf16
+    constexpr uint32_t A_BYTES = (180u * ROW_BYTES + 1023u) & ~1023u;    // 10 x 18 halo pixels, 1024-aligned slot
+    constexpr uint32_t B_BYTES = (uint32_t)COUT * ROW_BYTES;  // one tap of the weight matrix
+    const uint32_t S = (uint32_t)p.stages;                    // halo ring slots (even)
+    const uint32_t sB = sbase;                                // 9 resident weight sub-tiles
+    const uint32_t sA = sB + 9u * B_BYTES;                    // S halo slots
+    const uint32_t out_base = sA + S * A_BYTES;
+    const uint32_t bar_base = out_base + 8u * (uint32_t)p.ngroups * p.stage_out_bytes;
+    // barriers: full[0..S), empty[S..2S), tmem_full[2S..2S+8), tmem_empty[2S+8..2S+16), weights at 2S+16
+    const uint32_t bfull = bar_base + 8u * (2u * S + 16u);
+    const uint32_t tmem_slot = bar_base + 8u * (2u * S + 18u);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    float* sbias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - raw));
+    for (int i = threadIdx.x; i < COUT; i += NT_3WG) sbias[i] = p.bias ? p.bias[i] : 0.f;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); if (p.tma_store) tma_prefetch_desc(&tmY); }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t i = 0; i < S; ++i) { mbar_init(bar_base + 8u * i, 1); mbar_init(bar_base + 8u * (S + i), 1); }
+        for (uint32_t i = 0; i < 8; ++i) { mbar_init(bar_base + 8u * (2u * S + i), 1); mbar_init(bar_base + 8u * (2u * S + 8u + i), 4u * (uint32_t)p.csplit); }
+        mbar_init(bfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            mbar_expect_tx(bfull, 9u * B_BYTES);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(sB + (uint32_t)tap * B_BYTES, &tmB, bfull, tap * p.Cin, 0);
+        }
+        __syncwarp();
+        uint32_t stage = 0, phase = 0;
+        int tn = 0;
+        TileCur tc;
+        tc.init(p, blockIdx.x, (int)gridDim.x);
+        for (int t = blockIdx.x; t < p.num_tiles; t += (int)gridDim.x, tc.step(p)) {
+            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt;
+            const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (S + stage);
+            mbar_wait(empty, phase ^ 1u, p.dbg, 1);
+            if (lane == 0) trace(p.dbg, 0, tn, 1);
+            if (elect_one()) {
+                mbar_expect_tx(full, p.halo_tx);
+                tma_load_4d(sA + stage * A_BYTES, &tmA, full, p.x_coff, x0 - 1, y0 - 1, b0);
+            }
+            __syncwarp();
+            if (lane == 0) trace(p.dbg, 0, tn, 2);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == 1 || warp == 3) {
+        // ================= MMA issuers: warp 1 takes the even local tiles, warp 3 the odd ones =================
+        constexpr uint32_t ROW16 = ROW_BYTES >> 4, A16 = A_BYTES >> 4, B16 = B_BYTES >> 4;
+        const uint32_t pipe = (uint32_t)warp >> 1;
+        const uint64_t dA = make_smem_desc(0, 10u * ROW16, p.layout_type);      // 8-row groups one halo row apart
+        const uint64_t dB = make_smem_desc(0, p.sbo16, p.layout_type);
+        const uint32_t a_hi = (uint32_t)(dA >> 32), b_hi = (uint32_t)(dB >> 32);
+        const uint32_t a_lo0 = (uint32_t)dA + (sA >> 4), b_lo0 = (uint32_t)dB + (sB >> 4);
+        const uint32_t NACC = (uint32_t)p.nacc;
+        uint32_t stage = pipe, phase = 0, acc = pipe, acc_phase = 0;          // S and NACC are even and >= 2
+        int tn = 0;
+        mbar_wait(bfull, 0, p.dbg, 5);
+        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += 2 * (int)gridDim.x) {
+            const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 8u + acc);
+            const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (S + stage);
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
+            mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
+            if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 10);
+            mbar_wait(full, phase, p.dbg, 3);
+            tc_fence_after();
+            if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 11);
+            if (elect_one()) {
+                const uint32_t a_slot = a_lo0 + stage * A16;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t a_lo = a_slot + (uint32_t)((tap / 3) * 10 + (tap % 3)) * ROW16;   // tap shift in pixel rows
+                    const uint32_t b_lo = b_lo0 + (uint32_t)tap * B16;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k)
+                        umma_bf16_ab(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, p.idesc, (tap | k) ? 1u : 0u);
+                }
+                umma_commit(empty);
+                umma_commit(tfull);
+            }
+            __syncwarp();
+            if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 12);
+            stage += 2; if (stage >= S) { stage -= S; phase ^= 1u; }
+            acc += 2;   if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
+        }
+    } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
+        epilogue_role(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+    if (p.dbg && threadIdx.x == 0) {
+        const unsigned long long g = gtimer(); const long long c = clock64();
+        int* e = p.dbg + 2048 + blockIdx.x * 8;
+        e[4] = (int)(g & 0xffffffffull); e[5] = (int)(g >> 32); e[6] = (int)(c & 0xffffffffll); e[7] = (int)(c >> 32);
     }
 }
 
@@ -593,6 +766,13 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
             const long long tiles = (long long)yre_cdiv(Wo, tw) * yre_cdiv(Ho, th) * yre_cdiv(B, tb);
             if (best < 0 || tiles < best) { best = tiles; btw = tw; bth = th; btb = tb; }
         }
+    // weight-stationary halo kernel: small-channel 3x3 stride-1 convs whose 8x16 patches tile the map well
+    {
+        const long long htiles = (long long)yre_cdiv(Wo, 8) * yre_cdiv(Ho, 16) * B;
+        p.halo = d.k == 3 && d.stride == 1 && p.kchunks == 1 && (Cout == 64 || Cout == 32) &&
+                 htiles * 3 <= best * 4 && env_int("YRE_TC_HALO", 1) != 0;
+        if (p.halo) { btw = 8; bth = 16; btb = 1; best = htiles; }
+    }
     p.tw = btw; p.th = bth; p.tb = btb;
     p.tiles_x = yre_cdiv(Wo, btw); p.tiles_y = yre_cdiv(Ho, bth); p.tiles_b = yre_cdiv(B, btb);
     const long long mtiles = best;
@@ -607,10 +787,15 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     while (bn >= 64 && bn % 32 == 0 && mtiles * (Cout / bn) < sms) bn /= 2;
     const int force_bn = env_int("YRE_TC_BLOCK_N", 0);
     if (force_bn >= 16 && force_bn <= 256 && force_bn % 16 == 0 && Cout % force_bn == 0) bn = force_bn;
+    if (p.halo) bn = Cout;
     p.block_n = bn;
     p.tiles_n = Cout / bn;
     p.num_tiles = (int)(mtiles * p.tiles_n);
     p.a_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
+    if (p.halo) {
+        p.halo_tx = (uint32_t)(10 * 18 * p.block_k * 2);
+        p.a_bytes = (p.halo_tx + 1023u) & ~1023u;
+    }
     p.b_bytes = (uint32_t)(bn * p.block_k * 2);
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
     // bf16 outputs leave through a swizzled staging tile + TMA store; fp32 outputs (raw head logits) store directly
@@ -627,7 +812,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     // With one buffer per tile-group the group idles while its buffer is refilled, so keep nacc >= 2 * tgroups;
     // where TMEM only holds 2-3 buffers, split the chunks of each tile over the warpgroups instead.
     p.nthreads = bn <= 64 ? NT_3WG : NT_2WG;
-    { const int f = env_int("YRE_TC_THREADS", 0); if (f == NT_2WG || f == NT_3WG) p.nthreads = f; }
+    { const int f = env_int("YRE_TC_THREADS", 0); if ((f == NT_2WG || f == NT_3WG) && !p.halo) p.nthreads = f; }
     const int maxg = (p.nthreads / 32 - 4) / 4;
     if (bn <= 64)       { p.acc_stride = 64;  p.nacc = 6; p.tgroups = maxg; p.csplit = 1; }
     else if (bn <= 128) { p.acc_stride = 128; p.nacc = 4; p.tgroups = 2; p.csplit = 1; }
@@ -640,16 +825,18 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     const uint32_t n_stage_bufs = 8u * (uint32_t)p.ngroups;         // 4 warps x 2 buffers per group
     const uint32_t smem_cap = 227u * 1024u - 1024u - 256u - (uint32_t)Cout * 4u;   // alignment slack + barriers + bias copy
     int stages = (int)((smem_cap - n_stage_bufs * p.stage_out_bytes) / stage_bytes);
+    if (p.halo) stages = (int)((smem_cap - n_stage_bufs * p.stage_out_bytes - 9u * p.b_bytes) / p.a_bytes);
     if (stages > 8) stages = 8;
     const int force_st = env_int("YRE_TC_STAGES", 0);
     if (force_st >= 2 && force_st <= stages) stages = force_st;
     if (stages < 2) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: tile does not fit shared memory"); }
     // two (producer, MMA) pairs when the ring gives each at least 3 stages
-    p.npipes = (stages >= 6 && p.nacc % 2 == 0) ? 2 : 1;
+    p.npipes = (stages >= 6 && p.nacc % 2 == 0 && !p.halo) ? 2 : 1;
     { const int f = env_int("YRE_TC_PIPES", 0); if (f >= 1 && f <= 2 && p.nacc % f == 0 && stages >= 2 * f) p.npipes = f; }
-    if (p.npipes == 2) stages &= ~1;
+    if (p.npipes == 2 || p.halo) stages &= ~1;
     p.stages = stages;
     pl->smem = (size_t)stages * stage_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 16) + 32 + (size_t)Cout * 4 + 1024;
+    if (p.halo) pl->smem = 9 * (size_t)p.b_bytes + (size_t)stages * p.a_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 18) + 32 + (size_t)Cout * 4 + 1024;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     p.bias = d.bias; p.act = d.act;
     p.y = d.y.ptr; p.y_f32 = d.y.dtype == YRE_F32; p.y_ctot = d.y.C_total; p.y_coff = d.y.c_off;
@@ -672,6 +859,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         cuuint64_t gdim[4] = {(cuuint64_t)d.x.C_total, (cuuint64_t)d.x.W, (cuuint64_t)d.x.H, (cuuint64_t)d.x.B};
         cuuint64_t gstr[3] = {(cuuint64_t)d.x.C_total * 2, (cuuint64_t)d.x.W * d.x.C_total * 2, (cuuint64_t)d.x.H * d.x.W * d.x.C_total * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tb};
+        if (p.halo) { box[1] = 10; box[2] = 18; box[3] = 1; }      // patch + 1-pixel halo
         cuuint32_t est[4] = {1, 1, 1, 1};
         r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.x.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -720,6 +908,23 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
         attr_done = true;
     }
     const bool k64 = pl->p.block_k == 64;
+    if (pl->p.halo) {
+        static bool hattr_done = false;
+        if (!hattr_done) {
+            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            hattr_done = true;
+        }
+        const bool c64 = pl->p.Cout == 64;
+        if (k64) { if (c64) conv3_halo_kernel<4, 64><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+                   else     conv3_halo_kernel<4, 32><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p); }
+        else     { if (c64) conv3_halo_kernel<2, 64><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+                   else     conv3_halo_kernel<2, 32><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p); }
+        YRE_LAUNCH_CHECK("conv3_halo");
+        return YRE_OK;
+    }
     if (pl->p.nthreads == NT_3WG) {
         if (k64) conv_tc_kernel<4, NT_3WG><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
         else     conv_tc_kernel<2, NT_3WG><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
