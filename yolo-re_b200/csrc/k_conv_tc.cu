@@ -68,7 +68,8 @@ struct TcParams {
     int stw, sth, stb;              // the 32 pixels of one TMEM lane quarter as a (stb x sth x stw) sub-patch
     uint32_t stage_out_bytes;       // bytes of one per-warp staging buffer (32 rows x 32 ch x 2 = 2048)
     // weight-stationary halo variant (conv3_halo_kernel)
-    int halo;                       // 1: 3x3 stride-1 conv through the halo kernel
+    int halo;                       // 1: weight-stationary halo kernel, 2: halo kernel with streamed weights
+    int stages_b, tps;              // halo == 2: slots of the weight ring, filter taps per slot (1 or 3)
     uint32_t halo_tx;               // bytes one halo box delivers (10 x 18 pixels x BLOCK_K channels)
 };
 
@@ -145,6 +146,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Programmatic dependent launch: `pdl_launch_dependents` lets the next kernel of the stream start its prologue
+// (barrier init, TMEM alloc, tensor-map prefetch, bias copy) while this grid drains; `pdl_wait` blocks until the
+// previous grid has completed and its writes are visible.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -406,6 +413,7 @@ __global__ void __launch_bounds__(NT, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_launch_dependents();
     if (p.dbg && threadIdx.x == 0) {       // trace mode: per-CTA entry stamp (globaltimer ns, SM clock)
         const unsigned long long g = gtimer(); const long long c = clock64();
         int* e = p.dbg + 2048 + blockIdx.x * 8;
@@ -439,6 +447,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();      // everything above overlapped the previous kernel's tail; activations are read below
 
     const int kiters = p.taps * p.kchunks;
 
@@ -566,6 +575,7 @@ __global__ void __launch_bounds__(NT_3WG, 1)
 conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
+    pdl_launch_dependents();
     if (p.dbg && threadIdx.x == 0) {       // trace mode: per-CTA entry stamp (globaltimer ns, SM clock)
         const unsigned long long g = gtimer(); const long long c = clock64();
         int* e = p.dbg + 2048 + blockIdx.x * 8;
@@ -604,6 +614,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();      // everything above overlapped the previous kernel's tail; activations are read below
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -685,6 +696,190 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ---- halo variant with streamed weights (3x3 stride-1, Cin a multiple of 64, any Cout tile) -------------------
+// Same 8x16 patch + halo tile as above, but the weight matrix does not fit shared memory, so one {64, block_n}
+// weight box per (channel chunk, tap) streams through its own ring.  Per tile and channel chunk ONE halo box
+// replaces nine shifted activation boxes: the TMA write traffic into shared memory -- which shares the 128 B/clk
+// port with the UMMA operand reads and bounded the generic kernel at N = 128 (8 KB read + 8 KB written per
+// 64-cycle MMA) -- drops by the 4 KB of A per MMA.
+// Warp roles: warp 0 halo producer, warp 2 TMEM alloc + weight producer, warp 1 MMA issuer, warps 4.. epilogue.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
+conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmY, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    pdl_launch_dependents();
+    if (p.dbg && threadIdx.x == 0) {
+        const unsigned long long g = gtimer(); const long long c = clock64();
+        int* e = p.dbg + 2048 + blockIdx.x * 8;
+        e[0] = (int)(g & 0xffffffffull); e[1] = (int)(g >> 32); e[2] = (int)(c & 0xffffffffll); e[3] = (int)(c >> 32);
+    }
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t sbase = (raw + 1023u) & ~1023u;
+    constexpr uint32_t ROW_BYTES = 128, KSTEPS = 4;
+    constexpr uint32_t A_BYTES = (180u * ROW_BYTES + 1023u) & ~1023u;
+    const uint32_t SA = (uint32_t)p.stages, SB = (uint32_t)p.stages_b;
+    const uint32_t sA = sbase;
+    const uint32_t sB = sA + SA * A_BYTES;
+    const uint32_t out_base = sB + SB * (uint32_t)p.tps * p.b_bytes;
+    const uint32_t bar_base = out_base + 8u * (uint32_t)p.ngroups * p.stage_out_bytes;
+    // barriers: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB] tmem_full[8] tmem_empty[8]
+    const uint32_t barB = bar_base + 8u * (2u * SA);
+    const uint32_t bar_t = barB + 8u * (2u * SB);
+    const uint32_t tmem_slot = bar_t + 8u * 16u;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+    float* sbias = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16u - raw));
+    for (int i = threadIdx.x; i < p.Cout; i += NT) sbias[i] = p.bias ? p.bias[i] : 0.f;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); if (p.tma_store) tma_prefetch_desc(&tmY); }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t i = 0; i < 2u * SA; ++i) mbar_init(bar_base + 8u * i, 1);
+        for (uint32_t i = 0; i < 2u * SB; ++i) mbar_init(barB + 8u * i, 1);
+        for (uint32_t i = 0; i < 8; ++i) { mbar_init(bar_t + 8u * i, 1); mbar_init(bar_t + 8u * (8u + i), 4u * (uint32_t)p.csplit); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();      // everything above overlapped the previous kernel's tail; activations are read below
+
+    if (warp == 0) {
+        // ================= halo producer: one box per (tile, channel chunk), runs ahead by SA slots =================
+        uint32_t stage = 0, phase = 0;
+        int tn = 0;
+        TileCur tc;
+        tc.init(p, blockIdx.x, (int)gridDim.x);
+        for (int t = blockIdx.x; t < p.num_tiles; t += (int)gridDim.x, tc.step(p)) {
+            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (SA + stage);
+                mbar_wait(empty, phase ^ 1u, p.dbg, 1);
+                if (lane == 0) trace(p.dbg, 0, tn, 1);
+                if (elect_one()) {
+                    mbar_expect_tx(full, p.halo_tx);
+                    tma_load_4d(sA + stage * A_BYTES, &tmA, full, p.x_coff + kc * 64, x0 - 1, y0 - 1, b0);
+                }
+                __syncwarp();
+                if (lane == 0) trace(p.dbg, 0, tn, 2);
+                if (++stage == SA) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 2) {
+        // ================= weight producer: tps {64, block_n} boxes (filter taps) per ring slot =================
+        uint32_t stage = 0, phase = 0;
+        const uint32_t slot_bytes = (uint32_t)p.tps * p.b_bytes;
+        TileCur tc;
+        tc.init(p, blockIdx.x, (int)gridDim.x);
+        for (int t = blockIdx.x; t < p.num_tiles; t += (int)gridDim.x, tc.step(p)) {
+            const int n0 = tc.nt * p.block_n;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                for (int tap = 0; tap < 9; tap += p.tps) {
+                    const uint32_t full = barB + 8u * stage, empty = barB + 8u * (SB + stage);
+                    mbar_wait(empty, phase ^ 1u, p.dbg, 6);
+                    if (elect_one()) {
+                        mbar_expect_tx(full, slot_bytes);
+                        for (int i = 0; i < p.tps; ++i)
+                            tma_load_2d(sB + stage * slot_bytes + (uint32_t)i * p.b_bytes, &tmB, full, (tap + i) * p.Cin + kc * 64, n0);
+                    }
+                    __syncwarp();
+                    if (++stage == SB) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t ROW16 = ROW_BYTES >> 4, A16 = A_BYTES >> 4;
+        const uint64_t dA = make_smem_desc(0, 10u * ROW16, p.layout_type);      // 8-row groups one halo row apart
+        const uint64_t dB = make_smem_desc(0, p.sbo16, p.layout_type);
+        const uint32_t a_hi = (uint32_t)(dA >> 32), b_hi = (uint32_t)(dB >> 32);
+        const uint32_t a_lo0 = (uint32_t)dA + (sA >> 4), b_lo0 = (uint32_t)dB + (sB >> 4);
+        const uint32_t b16 = p.b_bytes >> 4;
+        const uint32_t NACC = (uint32_t)p.nacc;
+        uint32_t sa = 0, pha = 0, sb = 0, phb = 0, acc = 0, acc_phase = 0;
+        int tn = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += (int)gridDim.x) {
+            const uint32_t tfull = bar_t + 8u * acc, tempty = bar_t + 8u * (8u + acc);
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
+            mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
+            if (lane == 0) trace(p.dbg, 1, tn, 10);
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(bar_base + 8u * sa, pha, p.dbg, 3);
+                const uint32_t a_slot = a_lo0 + sa * A16;
+                if (p.tps == 3) {
+#pragma unroll
+                    for (int tap0 = 0; tap0 < 9; tap0 += 3) {
+                        mbar_wait(barB + 8u * sb, phb, p.dbg, 7);
+                        tc_fence_after();
+                        if (lane == 0) trace(p.dbg, 1, tn, 11);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) {
+                                const uint32_t a_lo = a_slot + (uint32_t)((tap0 / 3) * 10 + i) * ROW16;      // tap shift in pixel rows
+                                const uint32_t b_lo = b_lo0 + (sb * 3u + (uint32_t)i) * b16;
+#pragma unroll
+                                for (uint32_t k = 0; k < KSTEPS; ++k)
+                                    umma_bf16_ab(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, p.idesc, (kc | tap0 | i | (int)k) ? 1u : 0u);
+                            }
+                            umma_commit(barB + 8u * (SB + sb));                  // weight slot free when these MMAs retire
+                            if (tap0 == 6) {
+                                umma_commit(bar_base + 8u * (SA + sa));          // halo slot free
+                                if (kc == p.kchunks - 1) umma_commit(tfull);    // accumulator complete -> epilogue
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) trace(p.dbg, 1, tn, 12);
+                        if (++sb == SB) { sb = 0; phb ^= 1u; }
+                    }
+                } else {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(barB + 8u * sb, phb, p.dbg, 7);
+                        tc_fence_after();
+                        if (lane == 0) trace(p.dbg, 1, tn, 11);
+                        if (elect_one()) {
+                            const uint32_t a_lo = a_slot + (uint32_t)((tap / 3) * 10 + (tap % 3)) * ROW16;
+                            const uint32_t b_lo = b_lo0 + sb * b16;
+#pragma unroll
+                            for (uint32_t k = 0; k < KSTEPS; ++k)
+                                umma_bf16_ab(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, p.idesc, (kc | tap | (int)k) ? 1u : 0u);
+                            umma_commit(barB + 8u * (SB + sb));
+                            if (tap == 8) {
+                                umma_commit(bar_base + 8u * (SA + sa));
+                                if (kc == p.kchunks - 1) umma_commit(tfull);
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) trace(p.dbg, 1, tn, 12);
+                        if (++sb == SB) { sb = 0; phb ^= 1u; }
+                    }
+                }
+                if (++sa == SA) { sa = 0; pha ^= 1u; }
+            }
+            if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
+        epilogue_role(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_t, bar_t + 64u);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+    if (p.dbg && threadIdx.x == 0) {
+        const unsigned long long g = gtimer(); const long long c = clock64();
+        int* e = p.dbg + 2048 + blockIdx.x * 8;
+        e[4] = (int)(g & 0xffffffffull); e[5] = (int)(g >> 32); e[6] = (int)(c & 0xffffffffll); e[7] = (int)(c >> 32);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -719,6 +914,18 @@ struct ConvTcPlan {
     int grid;
     size_t smem;
 };
+
+template <typename K>
+static cudaError_t launch_tc(K kernel, int grid, int block, size_t smem, cudaStream_t s, const ConvTcPlan* pl) {
+    static const int pdl = env_int("YRE_TC_PDL", 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, pl->tmA, pl->tmB, pl->tmY, pl->p);
+}
 
 int conv_tc_eligible(const yre_conv_desc& d, char* why, size_t n) {
 #define NOPE(msg) do { if (why && n) snprintf(why, n, "%s", msg); return 0; } while (0)
@@ -771,6 +978,11 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         const long long htiles = (long long)yre_cdiv(Wo, 8) * yre_cdiv(Ho, 16) * B;
         p.halo = d.k == 3 && d.stride == 1 && p.kchunks == 1 && (Cout == 64 || Cout == 32) &&
                  htiles * 3 <= best * 4 && env_int("YRE_TC_HALO", 1) != 0;
+        // larger layers: streamed weights; worth it while the 8x16 patches waste less than the halo saves
+        // (measured at batch 64: +5..8% on the 80x80 maps that tile exactly, a loss on 40x40 where a sixth of the
+        //  patch rows is padding -- so by default only maps without patch waste take this path)
+        if (!p.halo && d.k == 3 && d.stride == 1 && p.block_k == 64 && htiles * 100 <= best * env_int("YRE_TC_HALO_SLACK", 100) &&
+            env_int("YRE_TC_HALO", 2) >= 2) p.halo = 2;
         if (p.halo) { btw = 8; bth = 16; btb = 1; best = htiles; }
     }
     p.tw = btw; p.th = bth; p.tb = btb;
@@ -787,7 +999,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     while (bn >= 64 && bn % 32 == 0 && mtiles * (Cout / bn) < sms) bn /= 2;
     const int force_bn = env_int("YRE_TC_BLOCK_N", 0);
     if (force_bn >= 16 && force_bn <= 256 && force_bn % 16 == 0 && Cout % force_bn == 0) bn = force_bn;
-    if (p.halo) bn = Cout;
+    if (p.halo == 1) bn = Cout;
     p.block_n = bn;
     p.tiles_n = Cout / bn;
     p.num_tiles = (int)(mtiles * p.tiles_n);
@@ -812,7 +1024,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     // With one buffer per tile-group the group idles while its buffer is refilled, so keep nacc >= 2 * tgroups;
     // where TMEM only holds 2-3 buffers, split the chunks of each tile over the warpgroups instead.
     p.nthreads = bn <= 64 ? NT_3WG : NT_2WG;
-    { const int f = env_int("YRE_TC_THREADS", 0); if ((f == NT_2WG || f == NT_3WG) && !p.halo) p.nthreads = f; }
+    { const int f = env_int("YRE_TC_THREADS", 0); if ((f == NT_2WG || f == NT_3WG) && p.halo != 1) p.nthreads = f; }
     const int maxg = (p.nthreads / 32 - 4) / 4;
     if (bn <= 64)       { p.acc_stride = 64;  p.nacc = 6; p.tgroups = maxg; p.csplit = 1; }
     else if (bn <= 128) { p.acc_stride = 128; p.nacc = 4; p.tgroups = 2; p.csplit = 1; }
@@ -825,18 +1037,35 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     const uint32_t n_stage_bufs = 8u * (uint32_t)p.ngroups;         // 4 warps x 2 buffers per group
     const uint32_t smem_cap = 227u * 1024u - 1024u - 256u - (uint32_t)Cout * 4u;   // alignment slack + barriers + bias copy
     int stages = (int)((smem_cap - n_stage_bufs * p.stage_out_bytes) / stage_bytes);
-    if (p.halo) stages = (int)((smem_cap - n_stage_bufs * p.stage_out_bytes - 9u * p.b_bytes) / p.a_bytes);
+    if (p.halo == 1) stages = (int)((smem_cap - n_stage_bufs * p.stage_out_bytes - 9u * p.b_bytes) / p.a_bytes);
     if (stages > 8) stages = 8;
+    if (p.halo == 2) {
+        // weight ring: three taps per slot when that still leaves >= 3 slots (fewer, longer MMA batches per
+        // mbarrier wait -- a single issuing thread needs ~450 cycles per wait + 4 MMAs), else one tap per slot
+        const uint32_t room = smem_cap - n_stage_bufs * p.stage_out_bytes - 256u;
+        int sa = 2;
+        p.tps = ((room - 2u * p.a_bytes) / (3u * p.b_bytes) >= 3) ? 3 : 1;
+        { const int f = env_int("YRE_TC_HALO_TPS", 0); if (f == 1 || f == 3) p.tps = f; }
+        int sb = (int)((room - 2u * p.a_bytes) / ((uint32_t)p.tps * p.b_bytes));
+        if (sb > (p.tps == 3 ? 4 : 8)) {           // room to spare: a third halo slot
+            const int sb3 = (int)((room - 3u * p.a_bytes) / ((uint32_t)p.tps * p.b_bytes));
+            if (sb3 >= (p.tps == 3 ? 3 : 5)) { sa = 3; sb = sb3; }
+        }
+        if (sb > 8) sb = 8;
+        if (sb < 2) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: halo tile does not fit shared memory"); }
+        stages = sa; p.stages_b = sb;
+    }
     const int force_st = env_int("YRE_TC_STAGES", 0);
     if (force_st >= 2 && force_st <= stages) stages = force_st;
     if (stages < 2) { delete pl; YRE_FAIL(YRE_EUNSUPPORTED, "conv_tc: tile does not fit shared memory"); }
     // two (producer, MMA) pairs when the ring gives each at least 3 stages
     p.npipes = (stages >= 6 && p.nacc % 2 == 0 && !p.halo) ? 2 : 1;
     { const int f = env_int("YRE_TC_PIPES", 0); if (f >= 1 && f <= 2 && p.nacc % f == 0 && stages >= 2 * f) p.npipes = f; }
-    if (p.npipes == 2 || p.halo) stages &= ~1;
+    if (p.npipes == 2 || p.halo == 1) stages &= ~1;
     p.stages = stages;
     pl->smem = (size_t)stages * stage_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 16) + 32 + (size_t)Cout * 4 + 1024;
-    if (p.halo) pl->smem = 9 * (size_t)p.b_bytes + (size_t)stages * p.a_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 18) + 32 + (size_t)Cout * 4 + 1024;
+    if (p.halo == 2) pl->smem = (size_t)stages * p.a_bytes + (size_t)p.stages_b * p.tps * p.b_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 2 * p.stages_b + 16) + 32 + (size_t)Cout * 4 + 1024;
+    else if (p.halo) pl->smem = 9 * (size_t)p.b_bytes + (size_t)stages * p.a_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 18) + 32 + (size_t)Cout * 4 + 1024;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     p.bias = d.bias; p.act = d.act;
     p.y = d.y.ptr; p.y_f32 = d.y.dtype == YRE_F32; p.y_ctot = d.y.C_total; p.y_coff = d.y.c_off;
@@ -908,6 +1137,18 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
         attr_done = true;
     }
     const bool k64 = pl->p.block_k == 64;
+    if (pl->p.halo == 2) {
+        static bool sattr_done = false;
+        if (!sattr_done) {
+            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_stream_kernel<NT_2WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_stream_kernel<NT_3WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            sattr_done = true;
+        }
+        if (pl->p.nthreads == NT_3WG) YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_3WG>, pl->grid, NT_3WG, pl->smem, s, pl));
+        else                          YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_2WG>, pl->grid, NT_2WG, pl->smem, s, pl));
+        YRE_LAUNCH_CHECK("conv3_halo_stream");
+        return YRE_OK;
+    }
     if (pl->p.halo) {
         static bool hattr_done = false;
         if (!hattr_done) {
@@ -918,19 +1159,19 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
             hattr_done = true;
         }
         const bool c64 = pl->p.Cout == 64;
-        if (k64) { if (c64) conv3_halo_kernel<4, 64><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
-                   else     conv3_halo_kernel<4, 32><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p); }
-        else     { if (c64) conv3_halo_kernel<2, 64><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
-                   else     conv3_halo_kernel<2, 32><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p); }
+        if (k64) { if (c64) YRE_CUDA(launch_tc(conv3_halo_kernel<4, 64>, pl->grid, NT_3WG, pl->smem, s, pl));
+                   else     YRE_CUDA(launch_tc(conv3_halo_kernel<4, 32>, pl->grid, NT_3WG, pl->smem, s, pl)); }
+        else     { if (c64) YRE_CUDA(launch_tc(conv3_halo_kernel<2, 64>, pl->grid, NT_3WG, pl->smem, s, pl));
+                   else     YRE_CUDA(launch_tc(conv3_halo_kernel<2, 32>, pl->grid, NT_3WG, pl->smem, s, pl)); }
         YRE_LAUNCH_CHECK("conv3_halo");
         return YRE_OK;
     }
     if (pl->p.nthreads == NT_3WG) {
-        if (k64) conv_tc_kernel<4, NT_3WG><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
-        else     conv_tc_kernel<2, NT_3WG><<<pl->grid, NT_3WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_3WG>, pl->grid, NT_3WG, pl->smem, s, pl));
+        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_3WG>, pl->grid, NT_3WG, pl->smem, s, pl));
     } else {
-        if (k64) conv_tc_kernel<4, NT_2WG><<<pl->grid, NT_2WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
-        else     conv_tc_kernel<2, NT_2WG><<<pl->grid, NT_2WG, pl->smem, s>>>(pl->tmA, pl->tmB, pl->tmY, pl->p);
+        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG>, pl->grid, NT_2WG, pl->smem, s, pl));
+        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG>, pl->grid, NT_2WG, pl->smem, s, pl));
     }
     YRE_LAUNCH_CHECK("conv_tc");
     return YRE_OK;
