@@ -35,6 +35,9 @@ BIG = [
     (64, 160, 160, 64, 0, 32, 32, 3, 1, 1, 0, 0),     # channel window of a wider buffer, BLOCK_K=32
     (16, 160, 160, 64, 0, 32, 32, 3, 1, 1, 0, 0),
     (64, 160, 160, 64, 32, 32, 32, 3, 1, 1, 0, 0),
+    (5, 80, 72, 128, 0, 128, 256, 3, 1, 1, 1, 0),     # 20: halo-stream pairs, odd patch count (last pair half empty), residual
+    (64, 80, 80, 128, 0, 128, 128, 3, 1, 1, 0, 0),    # 21: halo-stream pairs
+    (64, 80, 80, 256, 0, 256, 256, 3, 1, 1, 1, 0),    # 22: halo-stream pairs, 2 N tiles, 4 channel chunks
 ]
 
 

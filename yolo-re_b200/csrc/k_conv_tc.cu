@@ -70,6 +70,9 @@ struct TcParams {
     // weight-stationary halo variant (conv3_halo_kernel)
     int halo;                       // 1: weight-stationary halo kernel, 2: halo kernel with streamed weights
     int stages_b, tps;              // halo == 2: slots of the weight ring, filter taps per slot (1 or 3)
+    // halo == 2 schedules UNITS: unit P -> N tile P / upn, patches npair * (P % upn) + {0 .. npair-1} (M index, x fastest).
+    // npair == 2: two patches share every weight box (two accumulators fed per box, half the weight traffic per pixel).
+    int npair, upn, num_units, mtiles;
     uint32_t halo_tx;               // bytes one halo box delivers (10 x 18 pixels x BLOCK_K channels)
 };
 
@@ -344,8 +347,19 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
         int tn = 0;
         TileCur tc;
         tc.init(p, blockIdx.x + tg * (int)gridDim.x, (int)(G * gridDim.x));
-        for (int t = blockIdx.x + tg * (int)gridDim.x; t < p.num_tiles; t += (int)(G * gridDim.x), tc.step(p)) {
-            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt * p.tb, n0 = tc.nt * p.block_n;
+        const bool units = p.halo == 2;          // unit schedule of conv3_halo_stream_kernel (see TcParams)
+        for (int t = blockIdx.x + tg * (int)gridDim.x, j = tg; ; t += (int)(G * gridDim.x), j += (int)G, tc.step(p)) {
+            int x0, y0, b0, n0;
+            if (units) {
+                const int P = (int)blockIdx.x + (j / p.npair) * (int)gridDim.x;
+                if (P >= p.num_units) break;
+                const int m = p.npair * (P % p.upn) + (j % p.npair);
+                const int r = m / p.tiles_x;
+                x0 = (m % p.tiles_x) * p.tw; y0 = (r % p.tiles_y) * p.th; b0 = r / p.tiles_y; n0 = (P / p.upn) * p.block_n;
+            } else {
+                if (t >= p.num_tiles) break;
+                x0 = tc.xt * p.tw; y0 = tc.yt * p.th; b0 = tc.bt * p.tb; n0 = tc.nt * p.block_n;
+            }
             const int x = x0 + xx, y = y0 + yy, b = b0 + bi;
             const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
             const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
@@ -720,7 +734,8 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr uint32_t A_BYTES = (180u * ROW_BYTES + 1023u) & ~1023u;
     const uint32_t SA = (uint32_t)p.stages, SB = (uint32_t)p.stages_b;
     const uint32_t sA = sbase;
-    const uint32_t sB = sA + SA * A_BYTES;
+    const uint32_t NPAIR = (uint32_t)p.npair;
+    const uint32_t sB = sA + SA * NPAIR * A_BYTES;
     const uint32_t out_base = sB + SB * (uint32_t)p.tps * p.b_bytes;
     const uint32_t bar_base = out_base + 8u * (uint32_t)p.ngroups * p.stage_out_bytes;
     // barriers: fullA[SA] emptyA[SA] fullB[SB] emptyB[SB] tmem_full[8] tmem_empty[8]
@@ -750,20 +765,25 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     pdl_wait();      // everything above overlapped the previous kernel's tail; activations are read below
 
     if (warp == 0) {
-        // ================= halo producer: one box per (tile, channel chunk), runs ahead by SA slots =================
+        // ================= halo producer: npair boxes per (unit, channel chunk), runs ahead by SA slots =================
         uint32_t stage = 0, phase = 0;
         int tn = 0;
-        TileCur tc;
-        tc.init(p, blockIdx.x, (int)gridDim.x);
-        for (int t = blockIdx.x; t < p.num_tiles; t += (int)gridDim.x, tc.step(p)) {
-            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt;
+        for (int P = blockIdx.x; P < p.num_units; P += (int)gridDim.x) {
+            const int mp = P % p.upn;
+            int x0[2], y0[2], b0[2];
+            for (uint32_t h = 0; h < NPAIR; ++h) {
+                const int m = (int)NPAIR * mp + (int)h;
+                const int xt = m % p.tiles_x, r = m / p.tiles_x;
+                x0[h] = xt * p.tw - 1; y0[h] = (r % p.tiles_y) * p.th - 1; b0[h] = r / p.tiles_y;   // b0 >= B for the odd patch out: zero-filled
+            }
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (SA + stage);
                 mbar_wait(empty, phase ^ 1u, p.dbg, 1);
                 if (lane == 0) trace(p.dbg, 0, tn, 1);
                 if (elect_one()) {
-                    mbar_expect_tx(full, p.halo_tx);
-                    tma_load_4d(sA + stage * A_BYTES, &tmA, full, p.x_coff + kc * 64, x0 - 1, y0 - 1, b0);
+                    mbar_expect_tx(full, NPAIR * p.halo_tx);
+                    for (uint32_t h = 0; h < NPAIR; ++h)
+                        tma_load_4d(sA + (stage * NPAIR + h) * A_BYTES, &tmA, full, p.x_coff + kc * 64, x0[h], y0[h], b0[h]);
                 }
                 __syncwarp();
                 if (lane == 0) trace(p.dbg, 0, tn, 2);
@@ -774,10 +794,8 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ================= weight producer: tps {64, block_n} boxes (filter taps) per ring slot =================
         uint32_t stage = 0, phase = 0;
         const uint32_t slot_bytes = (uint32_t)p.tps * p.b_bytes;
-        TileCur tc;
-        tc.init(p, blockIdx.x, (int)gridDim.x);
-        for (int t = blockIdx.x; t < p.num_tiles; t += (int)gridDim.x, tc.step(p)) {
-            const int n0 = tc.nt * p.block_n;
+        for (int P = blockIdx.x; P < p.num_units; P += (int)gridDim.x) {
+            const int n0 = (P / p.upn) * p.block_n;
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 for (int tap = 0; tap < 9; tap += p.tps) {
                     const uint32_t full = barB + 8u * stage, empty = barB + 8u * (SB + stage);
@@ -800,68 +818,46 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const uint32_t a_hi = (uint32_t)(dA >> 32), b_hi = (uint32_t)(dB >> 32);
         const uint32_t a_lo0 = (uint32_t)dA + (sA >> 4), b_lo0 = (uint32_t)dB + (sB >> 4);
         const uint32_t b16 = p.b_bytes >> 4;
-        const uint32_t NACC = (uint32_t)p.nacc;
+        const uint32_t NACC = (uint32_t)p.nacc, TPS = (uint32_t)p.tps, astr = (uint32_t)p.acc_stride;
         uint32_t sa = 0, pha = 0, sb = 0, phb = 0, acc = 0, acc_phase = 0;
         int tn = 0;
-        for (int t = blockIdx.x; t < p.num_tiles; t += (int)gridDim.x) {
-            const uint32_t tfull = bar_t + 8u * acc, tempty = bar_t + 8u * (8u + acc);
-            const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
-            mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
+        for (int P = blockIdx.x; P < p.num_units; P += (int)gridDim.x) {
+            const uint32_t d_tmem = tmem_base + acc * astr;
+            for (uint32_t h = 0; h < NPAIR; ++h) mbar_wait(bar_t + 8u * (8u + acc + h), acc_phase ^ 1u, p.dbg, 2);
             if (lane == 0) trace(p.dbg, 1, tn, 10);
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 mbar_wait(bar_base + 8u * sa, pha, p.dbg, 3);
-                const uint32_t a_slot = a_lo0 + sa * A16;
-                if (p.tps == 3) {
-#pragma unroll
-                    for (int tap0 = 0; tap0 < 9; tap0 += 3) {
-                        mbar_wait(barB + 8u * sb, phb, p.dbg, 7);
-                        tc_fence_after();
-                        if (lane == 0) trace(p.dbg, 1, tn, 11);
-                        if (elect_one()) {
-#pragma unroll
-                            for (int i = 0; i < 3; ++i) {
-                                const uint32_t a_lo = a_slot + (uint32_t)((tap0 / 3) * 10 + i) * ROW16;      // tap shift in pixel rows
-                                const uint32_t b_lo = b_lo0 + (sb * 3u + (uint32_t)i) * b16;
+                const uint32_t a_slot = a_lo0 + sa * NPAIR * A16;
+                for (uint32_t tap0 = 0; tap0 < 9; tap0 += TPS) {
+                    mbar_wait(barB + 8u * sb, phb, p.dbg, 7);
+                    tc_fence_after();
+                    if (lane == 0) trace(p.dbg, 1, tn, 11);
+                    if (elect_one()) {
+                        for (uint32_t i = 0; i < TPS; ++i) {
+                            const uint32_t tap = tap0 + i;
+                            const uint32_t shift = ((tap / 3u) * 10u + (tap % 3u)) * ROW16;      // tap shift in pixel rows
+                            const uint32_t b_lo = b_lo0 + (sb * TPS + i) * b16;
+                            for (uint32_t h = 0; h < NPAIR; ++h) {
+                                const uint32_t a_lo = a_slot + h * A16 + shift;
 #pragma unroll
                                 for (uint32_t k = 0; k < KSTEPS; ++k)
-                                    umma_bf16_ab(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, p.idesc, (kc | tap0 | i | (int)k) ? 1u : 0u);
-                            }
-                            umma_commit(barB + 8u * (SB + sb));                  // weight slot free when these MMAs retire
-                            if (tap0 == 6) {
-                                umma_commit(bar_base + 8u * (SA + sa));          // halo slot free
-                                if (kc == p.kchunks - 1) umma_commit(tfull);    // accumulator complete -> epilogue
+                                    umma_bf16_ab(d_tmem + h * astr, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, p.idesc, ((uint32_t)kc | tap | k) ? 1u : 0u);
                             }
                         }
-                        __syncwarp();
-                        if (lane == 0) trace(p.dbg, 1, tn, 12);
-                        if (++sb == SB) { sb = 0; phb ^= 1u; }
-                    }
-                } else {
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(barB + 8u * sb, phb, p.dbg, 7);
-                        tc_fence_after();
-                        if (lane == 0) trace(p.dbg, 1, tn, 11);
-                        if (elect_one()) {
-                            const uint32_t a_lo = a_slot + (uint32_t)((tap / 3) * 10 + (tap % 3)) * ROW16;
-                            const uint32_t b_lo = b_lo0 + sb * b16;
-#pragma unroll
-                            for (uint32_t k = 0; k < KSTEPS; ++k)
-                                umma_bf16_ab(d_tmem, a_lo + 2u * k, a_hi, b_lo + 2u * k, b_hi, p.idesc, (kc | tap | (int)k) ? 1u : 0u);
-                            umma_commit(barB + 8u * (SB + sb));
-                            if (tap == 8) {
-                                umma_commit(bar_base + 8u * (SA + sa));
-                                if (kc == p.kchunks - 1) umma_commit(tfull);
-                            }
+                        umma_commit(barB + 8u * (SB + sb));                      // weight slot free when these MMAs retire
+                        if (tap0 + TPS == 9) {
+                            umma_commit(bar_base + 8u * (SA + sa));              // halo slot free
+                            if (kc == p.kchunks - 1)                             // accumulators complete -> epilogue
+                                for (uint32_t h = 0; h < NPAIR; ++h) umma_commit(bar_t + 8u * (acc + h));
                         }
-                        __syncwarp();
-                        if (lane == 0) trace(p.dbg, 1, tn, 12);
-                        if (++sb == SB) { sb = 0; phb ^= 1u; }
                     }
+                    __syncwarp();
+                    if (lane == 0) trace(p.dbg, 1, tn, 12);
+                    if (++sb == SB) { sb = 0; phb ^= 1u; }
                 }
                 if (++sa == SA) { sa = 0; pha ^= 1u; }
             }
-            if (++acc == NACC) { acc = 0; acc_phase ^= 1u; }
+            acc += NPAIR; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
         epilogue_role(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_t, bar_t + 64u);
@@ -1000,9 +996,18 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     const int force_bn = env_int("YRE_TC_BLOCK_N", 0);
     if (force_bn >= 16 && force_bn <= 256 && force_bn % 16 == 0 && Cout % force_bn == 0) bn = force_bn;
     if (p.halo == 1) bn = Cout;
+    p.npair = 1;
+    if (p.halo == 2) {
+        // two patches per weight box when a 128-wide N tile exists and there are enough pairs to fill the machine
+        const int want = env_int("YRE_TC_HALO_PAIR", 1);
+        if (want && Cout % 128 == 0 && ((mtiles + 1) / 2) * (Cout / 128) >= sms) { p.npair = 2; bn = 128; }
+    }
     p.block_n = bn;
     p.tiles_n = Cout / bn;
     p.num_tiles = (int)(mtiles * p.tiles_n);
+    p.mtiles = (int)mtiles;
+    p.upn = (int)((mtiles + p.npair - 1) / p.npair);
+    p.num_units = p.upn * p.tiles_n;
     p.a_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
     if (p.halo) {
         p.halo_tx = (uint32_t)(10 * 18 * p.block_k * 2);
@@ -1032,6 +1037,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     else                { p.acc_stride = 256; p.nacc = 2; p.tgroups = 1; p.csplit = maxg; }
     { const int f = env_int("YRE_TC_TGROUPS", 0); if (f >= 1 && f <= maxg && p.nacc % f == 0) { p.tgroups = f; if (p.tgroups * p.csplit > maxg) p.csplit = 1; } }
     { const int f = env_int("YRE_TC_SPLIT", 0); if (f >= 1 && f * p.tgroups <= maxg) p.csplit = f; }
+    if (p.npair == 2) { p.nthreads = NT_2WG; p.acc_stride = 128; p.nacc = 4; p.tgroups = 2; p.csplit = 1; }   // group h <-> patch h
     while (p.csplit > 1 && p.csplit > (bn + 31) / 32) --p.csplit;   // every warpgroup owns at least one chunk
     p.ngroups = p.tgroups * p.csplit;
     const uint32_t n_stage_bufs = 8u * (uint32_t)p.ngroups;         // 4 warps x 2 buffers per group
@@ -1043,12 +1049,13 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         // weight ring: three taps per slot when that still leaves >= 3 slots (fewer, longer MMA batches per
         // mbarrier wait -- a single issuing thread needs ~450 cycles per wait + 4 MMAs), else one tap per slot
         const uint32_t room = smem_cap - n_stage_bufs * p.stage_out_bytes - 256u;
+        const uint32_t a_slot = (uint32_t)p.npair * p.a_bytes;
         int sa = 2;
-        p.tps = ((room - 2u * p.a_bytes) / (3u * p.b_bytes) >= 3) ? 3 : 1;
+        p.tps = ((room - 2u * a_slot) / (3u * p.b_bytes) >= (p.npair == 2 ? 2u : 3u)) ? 3 : 1;
         { const int f = env_int("YRE_TC_HALO_TPS", 0); if (f == 1 || f == 3) p.tps = f; }
-        int sb = (int)((room - 2u * p.a_bytes) / ((uint32_t)p.tps * p.b_bytes));
+        int sb = (int)((room - 2u * a_slot) / ((uint32_t)p.tps * p.b_bytes));
         if (sb > (p.tps == 3 ? 4 : 8)) {           // room to spare: a third halo slot
-            const int sb3 = (int)((room - 3u * p.a_bytes) / ((uint32_t)p.tps * p.b_bytes));
+            const int sb3 = (int)((room - 3u * a_slot) / ((uint32_t)p.tps * p.b_bytes));
             if (sb3 >= (p.tps == 3 ? 3 : 5)) { sa = 3; sb = sb3; }
         }
         if (sb > 8) sb = 8;
@@ -1064,7 +1071,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     if (p.npipes == 2 || p.halo == 1) stages &= ~1;
     p.stages = stages;
     pl->smem = (size_t)stages * stage_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 16) + 32 + (size_t)Cout * 4 + 1024;
-    if (p.halo == 2) pl->smem = (size_t)stages * p.a_bytes + (size_t)p.stages_b * p.tps * p.b_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 2 * p.stages_b + 16) + 32 + (size_t)Cout * 4 + 1024;
+    if (p.halo == 2) pl->smem = (size_t)stages * p.npair * p.a_bytes + (size_t)p.stages_b * p.tps * p.b_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 2 * p.stages_b + 16) + 32 + (size_t)Cout * 4 + 1024;
     else if (p.halo) pl->smem = 9 * (size_t)p.b_bytes + (size_t)stages * p.a_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 18) + 32 + (size_t)Cout * 4 + 1024;
     p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
     p.bias = d.bias; p.act = d.act;
@@ -1080,6 +1087,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         g_trace_buf = g_dbg;
     }
     pl->grid = p.num_tiles < sms ? p.num_tiles : sms;
+    if (p.halo == 2) pl->grid = p.num_units < sms ? p.num_units : sms;
 
     // ---- tensor maps ----
     const CUtensorMapSwizzle swz = p.block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;

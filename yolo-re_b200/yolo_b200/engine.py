@@ -287,16 +287,23 @@ class Plan:
         return out
 
     def towers(self, box, cls, dfl, feats: list[V], strides: list[float], nc: int):
-        """One head: per level merged first 3x3 (box||cls), the two towers, fp32 raw logits; then K6."""
+        """One head: per level first 3x3 of box and cls (merged into one GEMM on the small levels), the two
+        towers, fp32 raw logits; then K6."""
         raws = []
         for i, f in enumerate(feats):
             c2 = box[i][0].conv.out_channels
             c3 = cls[i][0].conv.out_channels
-            h1 = self.conv_merged([box[i][0], cls[i][0]], f)
             raw = self.alloc(f.H, f.W, 4 * REG_MAX + nc, dtype=L.F32)
-            hb = self.conv_m(box[i][1], h1.sl(0, c2))
+            if f.H % 16 == 0 and f.W % 8 == 0 and f.H * f.W >= 4096 and c3 % 128 == 0:
+                # large level: the 128-wide N tiles of the cls conv take the paired halo kernel (two patches per
+                # weight box); a merged 64+256 = 320-channel GEMM would fall back to 160-wide unpaired tiles
+                hb_in, hc_in = self.conv_m(box[i][0], f), self.conv_m(cls[i][0], f)
+            else:
+                h1 = self.conv_merged([box[i][0], cls[i][0]], f)
+                hb_in, hc_in = h1.sl(0, c2), h1.sl(c2, c3)
+            hb = self.conv_m(box[i][1], hb_in)
             self.conv_m(box[i][2], hb, out=raw.sl(0, 4 * REG_MAX))
-            hc = self.conv_m(cls[i][1], h1.sl(c2, c3))
+            hc = self.conv_m(cls[i][1], hc_in)
             self.conv_m(cls[i][2], hc, out=raw.sl(4 * REG_MAX, nc))
             raws.append(raw)
         A = sum(r.H * r.W for r in raws)
