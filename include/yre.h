@@ -163,6 +163,37 @@ typedef struct yre_nms_desc {
 size_t yre_nms_workspace_bytes(int32_t B, int32_t A);
 int    yre_nms_batched(const yre_nms_desc* d, yre_stream_t s);
 
+/* ---- K8/K9: the steps either side of the path -----------------------------------
+ * K8 replaces letterbox                                  scripts/detect.py:40-71
+ *             cv2.resize(INTER_LINEAR) on uint8          (OpenCV; 8-bit fixed point, bit-exact restatement)
+ *             BGR->RGB, HWC->CHW, .float() / 255         scripts/detect.py:223-227
+ * src: uint8 [h][w][3] (cv2.imread layout, rows `row_pitch` bytes apart) on the DEVICE.
+ * out_mode YRE_LB_F32_CHW: dst = float [3][S][S], channel order reversed (RGB), value / 255 -- the tensor the
+ *                          reference feeds to model(); YRE_LB_U8_HWC: dst = uint8 [S][S][3], what letterbox() returns.
+ * The geometry (un-padded size, padding) comes from yre_letterbox_geometry, which mirrors the reference's
+ * Python arithmetic including round-half-to-even. */
+enum { YRE_LB_F32_CHW = 0, YRE_LB_U8_HWC = 1 };
+typedef struct yre_letterbox_desc {
+    const uint8_t* src;
+    int32_t        h, w;
+    int64_t        row_pitch;
+    int32_t        new_shape;        /* S */
+    int32_t        new_w, new_h;     /* resized, un-padded size */
+    int32_t        top, left;        /* padding before the image */
+    uint8_t        color[4];         /* pad colour in SOURCE channel order (114,114,114), 4th byte unused */
+    int32_t        out_mode;
+    void*          dst;
+} yre_letterbox_desc;
+/* host helper: fills new_w/new_h/top/left of *d from (h, w, new_shape); ratio and the (pad_w, pad_h) pair the
+ * reference returns go to the optional outputs.  Fails with YRE_EINVAL when the padded size is not S x S. */
+int yre_letterbox_geometry(yre_letterbox_desc* d, double* ratio, int32_t* pad_w, int32_t* pad_h);
+int yre_letterbox_u8(const yre_letterbox_desc* d, yre_stream_t s);
+/* K9 replaces scale_boxes                                scripts/detect.py:74-109
+ * boxes: n rows of xyxy fp32, `row_stride` floats apart (6 for detection rows), updated in place:
+ * x = clamp((x - pad_w) / gain, 0, orig_w), y likewise -- fp32, true division, as torch does on the CPU. */
+int yre_scale_boxes(float* boxes, int32_t n, int32_t row_stride, float pad_w, float pad_h, float gain,
+                    float orig_w, float orig_h, yre_stream_t s);
+
 /* ---- flat launch plan -------------------------------------------------------------------------
  * Replaces the named-DAG interpreter loop of YOLO.forward  src/yolo/model/model.py:87-107
  * The host walks the module tree once, records every op (descriptors are copied, TMA tensor

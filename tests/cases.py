@@ -56,3 +56,35 @@ def at_threshold_pred(nc=4):
             row[4 + (k % nc)] = sc
             rows.append(row)
     return torch.tensor([rows], dtype=torch.float32)
+
+
+# ---- pre/post-processing cases: name -> (h, w, new_shape, seed) ---------------------------
+PREPROC_CASES = {
+    "vga": (480, 640, 640, 1),            # width already 640: no resize, pad top/bottom
+    "up_500x375": (375, 500, 640, 2),     # up-scaling
+    "hd": (1080, 1920, 640, 3),           # down-scaling, non-integer ratio
+    "area2x": (1280, 960, 640, 4),        # exact 2x down-scale -> cv2 switches to INTER_AREA
+    "odd": (333, 517, 640, 5),
+    "tiny_up": (100, 80, 640, 6),         # 6.4x up-scaling, many clipped border rows
+    "square": (640, 640, 640, 7),         # identity
+    "portrait_1280": (1280, 720, 1280, 8),
+    "odd_pad": (481, 641, 640, 9),        # odd padding -> top != bottom
+}
+
+
+def preproc_image(h: int, w: int, seed: int):
+    """Smooth-ish synthetic BGR image with full 0..255 range (seeded, numpy only)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (h // 8 + 2, w // 8 + 2, 3), dtype=np.uint8)
+    img = np.repeat(np.repeat(base, 8, 0), 8, 1)[:h, :w].astype(np.int32)
+    img += rng.integers(-24, 25, (h, w, 3), dtype=np.int32)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def preproc_boxes(S: int, seed: int, n: int = 64):
+    """xyxy boxes in letterboxed-input pixels, some outside the un-padded image so the clip matters."""
+    import numpy as np
+    rng = np.random.default_rng(1000 + seed)
+    c = rng.uniform(-20, S + 20, (n, 2)); wh = rng.uniform(2, S / 2, (n, 2))
+    return np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)

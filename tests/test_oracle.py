@@ -121,3 +121,58 @@ def test_bit_equal_to_reference(cfg, fix, request):
     pred = yr.permute(0, 2, 1).contiguous()
     for a, b in zip(non_max_suppression(pred, 0.25, 0.45), N.non_max_suppression(pred, 0.25, 0.45)):
         assert np.array_equal(a.numpy(), b)
+
+
+# ---- pre/post-processing oracle -------------------------------------------------------
+import hashlib  # noqa: E402
+
+from oracle import preproc_ref as P  # noqa: E402
+from tests.cases import PREPROC_CASES, preproc_boxes, preproc_image  # noqa: E402
+
+PRE_GOLD = np.load(Path(__file__).resolve().parent / "golden" / "preproc_cases.npz")
+
+
+@pytest.mark.parametrize("name", list(PREPROC_CASES))
+def test_preproc_oracle_matches_reference_fixture(name):
+    """oracle letterbox / preprocess / scale_boxes == what the REFERENCE's functions produced (make_golden_preproc.py)."""
+    h, w, S, seed = PREPROC_CASES[name]
+    img = preproc_image(h, w, seed)
+    lb, ratio, pad = P.letterbox(img, S)
+    assert lb.shape == (S, S, 3)
+    assert hashlib.sha256(lb.tobytes()).digest() == PRE_GOLD[f"{name}/sha"].tobytes()
+    assert np.array_equal(lb[[0, S // 3, S - 1]], PRE_GOLD[f"{name}/rows"])
+    x, _, _ = P.preprocess(img, S)
+    assert hashlib.sha256(x.tobytes()).digest() == PRE_GOLD[f"{name}/x_sha"].tobytes()
+    assert ratio[0] == PRE_GOLD[f"{name}/ratio"][0] and tuple(PRE_GOLD[f"{name}/pad"]) == pad
+    b = preproc_boxes(S, seed)
+    assert np.array_equal(P.scale_boxes(b, (S, S), (h, w), (ratio, pad)), PRE_GOLD[f"{name}/boxes_rp"])
+    assert np.array_equal(P.scale_boxes(b, (S, S), (h, w)), PRE_GOLD[f"{name}/boxes_none"])
+
+
+def test_resize_restatement_matches_cv2_when_available():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for h, w, dw, dh in [(37, 53, 1280, 894), (375, 500, 640, 480), (1079, 1919, 640, 360), (64, 48, 32, 24), (7, 9, 64, 50),
+                         (200, 300, 299, 199), (50, 50, 51, 49)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(P.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR)), (h, w, dw, dh)
+
+
+def test_letterbox_geometry_c_helper_matches_python_arithmetic():
+    """yre_letterbox_geometry (host arithmetic in libyre, no GPU) == the reference's Python rounding for many sizes."""
+    import ctypes as C
+    import yolo_b200  # noqa: F401
+    from yolo_b200 import _lib as L
+    rng = np.random.default_rng(3)
+    sizes = [(480, 640, 640), (481, 641, 640), (1, 1, 640), (5, 1000, 640), (1000, 5, 640), (1281, 1279, 1280)]
+    sizes += [(int(h), int(w), 640) for h, w in rng.integers(8, 4000, (300, 2))]
+    for h, w, S in sizes:
+        nw, nh, top, left, bottom, right, r, pad = P.letterbox_geometry(h, w, S)
+        d = L.LetterboxDesc(); d.h, d.w, d.new_shape = h, w, S
+        rr, pw, ph = C.c_double(), C.c_int32(), C.c_int32()
+        rc = L.lib().yre_letterbox_geometry(C.byref(d), C.byref(rr), C.byref(pw), C.byref(ph))
+        if nw <= 0 or nh <= 0:
+            assert rc != 0
+            continue
+        assert rc == 0, (h, w, S, L.lib().yre_last_error())
+        assert (d.new_w, d.new_h, d.top, d.left, rr.value, (pw.value, ph.value)) == (nw, nh, top, left, r, pad), (h, w, S)

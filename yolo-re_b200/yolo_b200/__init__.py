@@ -7,7 +7,8 @@ from ._lib import YreError, lib
 from .engine import precision
 from .model import BLOCKS, YOLO, ModelConfig, build_layers, parse_yaml
 from .nms import nms_raw, non_max_suppression
+from .preprocess import letterbox, preprocess, scale_boxes
 
 __version__ = "0.1.0"
 __all__ = ["YOLO", "non_max_suppression", "nms_raw", "precision", "YreError", "lib", "ModelConfig", "parse_yaml",
-           "build_layers", "BLOCKS"]
+           "build_layers", "BLOCKS", "letterbox", "preprocess", "scale_boxes"]

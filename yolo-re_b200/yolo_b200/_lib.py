@@ -45,6 +45,14 @@ class NmsDesc(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class LetterboxDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("row_pitch", C.c_int64),
+                ("new_shape", C.c_int32), ("new_w", C.c_int32), ("new_h", C.c_int32), ("top", C.c_int32),
+                ("left", C.c_int32), ("color", C.c_uint8 * 4), ("out_mode", C.c_int32), ("dst", C.c_void_p)]
+
+
+LB_F32_CHW, LB_U8_HWC = 0, 1
+
 # name -> (restype, argtypes); every symbol include/yre.h declares
 SYMBOLS = {
     "yre_version": (C.c_int, []),
@@ -61,6 +69,9 @@ SYMBOLS = {
     "yre_dfl_decode_score": (C.c_int, [C.POINTER(DecodeDesc), C.c_void_p]),
     "yre_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "yre_nms_batched": (C.c_int, [C.POINTER(NmsDesc), C.c_void_p]),
+    "yre_letterbox_geometry": (C.c_int, [C.POINTER(LetterboxDesc), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "yre_letterbox_u8": (C.c_int, [C.POINTER(LetterboxDesc), C.c_void_p]),
+    "yre_scale_boxes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "yre_plan_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "yre_plan_destroy": (None, [C.c_void_p]),
     "yre_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
