@@ -138,6 +138,29 @@ def test_yolov9_c_plan_wiring(yolov9_c, dry):
         assert (yy[:, :4] - ref[:, :4]).abs().max() < 2e-2 and (yy[:, 4:] - ref[:, 4:]).abs().max() < 2e-4
 
 
+def test_yolov9_c_main_only_plan_prunes_the_aux_branch(yolov9_c, dry):
+    """opt-in main_only compiles only what the main towers need (callers drop the aux half,
+    scripts/detect.py:239-241); default stays API-faithful (dual)."""
+    nodes, nc, sd = yolov9_c
+    m = YOLO.from_yaml(ROOT / "configs/models/yolov9-c.yaml")
+    m.load_state_dict(sd)
+    m.eval().set_precision("fp32")
+    x = G.fractal(1, 64, torch.Generator().manual_seed(5))
+    (_, ym_ref), _ = G.forward(nodes, nc, sd, x)
+    full = engine.compile_model(m, x)
+    m.main_only = True
+    p = engine.compile_model(m, x)
+    census = Counter(n for n, _ in p.op_table())
+    assert census.get("cbfuse_sum", 0) == 0 and census["stem"] == 1 and census["dfl_decode_score"] == 1
+    gf_full, gf_main = sum(f for _, f in full.op_table()), sum(f for _, f in p.op_table())
+    assert 0.40 < gf_main / gf_full < 0.46          # 102.1 of 237.6 GF: the main branch is gelan-c sized
+    X.run(p)
+    kind, y, raws = p.result
+    assert kind == "single" and len(raws) == 3
+    yy = y.permute(0, 2, 1)
+    assert (yy[:, :4] - ym_ref[:, :4]).abs().max() < 2e-2 and (yy[:, 4:] - ym_ref[:, 4:]).abs().max() < 2e-4
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_block_plans(dry, prec):
     """Stand-alone block calls (what the stage-wise GPU parity tests use) wire correctly."""

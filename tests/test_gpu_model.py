@@ -135,6 +135,24 @@ def test_yolov9c_dual_head_outputs(yolov9_c):
     assert (ym16[:, 4:].cpu() - ym_ref[:, 4:]).abs().mean() < 5e-3
 
 
+def test_yolov9c_main_only_equals_main_half(yolov9_c):
+    """Opt-in aux-branch pruning: same kernels on the same data, so the result equals the dual model's main half bit for bit."""
+    nodes, nc, sd = yolov9_c
+    x = G.fractal(2, 128, torch.Generator().manual_seed(10)).to(DEV)
+    for prec in ("fp32", "bf16"):
+        m = build("yolov9-c", sd, prec)
+        (_, ym), (_, rm) = m(x)
+        n_full = m._plans[next(iter(m._plans))].num_launches
+        m.main_only = True
+        y1, r1 = m(x)
+        n_main = [p for k, p in m._plans.items() if k[-1]][0].num_launches
+        assert n_main < 0.7 * n_full            # 134 of 215 launches
+        assert torch.equal(y1, ym) and all(torch.equal(a, b) for a, b in zip(r1, rm))
+        m.main_only = False
+        (_, ym2), _ = m(x)
+        assert torch.equal(ym2, ym)
+
+
 def test_state_dict_roundtrip_and_replan(gelan_c):
     nodes, nc, sd = gelan_c
     m = build("gelan-c", sd, "fp32")

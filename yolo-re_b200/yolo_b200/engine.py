@@ -322,8 +322,11 @@ class Plan:
         self.trace.append(("decode", dict(raws=raws, strides=list(strides), nc=nc, dfl_w=wd, y=y)))
         return y, raws
 
-    def detect(self, m, feats: list[V]):
+    def detect(self, m, feats: list[V], main_only: bool = False):
         strides = m.stride.tolist()
+        if main_only:                      # feats = the main half only; result looks like a single head's
+            y, raws = self.towers(m.main_box_convs, m.main_cls_convs, m.dfl2, feats, strides, m.num_classes)
+            return ("single", y, raws)
         if isinstance(m, DetectDFL):
             y, raws = self.towers(m.box_convs, m.cls_convs, m.dfl, feats, strides, m.num_classes)
             return ("single", y, raws)
@@ -465,6 +468,17 @@ def compile_model(model, x: torch.Tensor) -> Plan:
                     dest[s] = (n, off)
                 off += chan[s]
     cat_bufs: dict[str, V] = {}
+    # main_only (opt-in): every caller of a dual-head model drops the auxiliary half
+    # (scripts/detect.py:239-241, eval/evaluator.py:107-109); compile only what the main towers need.
+    needed, det_name, det_levels = None, names[-1], 0
+    if getattr(model, "main_only", False) and isinstance(model.layers[det_name], DualDetectDFL):
+        det_levels = model.layers[det_name].num_levels
+        needed, stack = {det_name}, list(srcs[det_name][det_levels:])
+        while stack:
+            s_ = stack.pop()
+            if s_ != "input" and s_ not in needed:
+                needed.add(s_)
+                stack.extend(srcs[s_])
 
     def out_for(n: str, H_: int, W_: int) -> V | None:
         if n not in dest:
@@ -477,7 +491,12 @@ def compile_model(model, x: torch.Tensor) -> Plan:
     vals: dict[str, object] = {}
     result = None
     for n in names:
+        if needed is not None and n not in needed:
+            continue
         m = model.layers[n]
+        if needed is not None and n == det_name:
+            vals[n] = result = p.detect(m, [vals[s] for s in srcs[n][det_levels:]], main_only=True)
+            continue
         ins = [("input" if s == "input" else vals[s]) for s in srcs[n]]
         single = isinstance(conn[n], str)
         if single and ins[0] == "input" or (not single and any(i == "input" for i in ins)):
@@ -532,7 +551,7 @@ def model_forward(model, x: torch.Tensor):
     if x.dim() != 4:
         raise ValueError("expected input [B,C,H,W]")
     x = x.contiguous().float()
-    key = (tuple(x.shape), x.device.index, model.precision)
+    key = (tuple(x.shape), x.device.index, model.precision, bool(getattr(model, "main_only", False)))
     p = model._plans.get(key)
     if p is not None and model.check_weights and p.weight_version != _weights_version(model):
         p = None
