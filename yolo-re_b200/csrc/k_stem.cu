@@ -7,6 +7,7 @@
 // the folded weights broadcast from shared memory (one weight read feeds 4 pixels).  Output is written channels-last (optionally as the 4 parity planes the
 // stride-2 tcgen05 conv that follows wants), 32 B per store.
 #include "yre_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -252,6 +253,148 @@ __global__ void __launch_bounds__(128, 3) stem_mma_kernel(const StemParams p, in
     }
 }
 
+// Stride-2 variant with a vectorised gather (W % 4 == 0): the first version spent ~800 instructions per
+// 16-pixel segment, most of them on scalar loads, bounds tests and index arithmetic, and ran at 57 % issue
+// utilisation with only 12 resident warps per SM (ncu, profiles/r01_notes.md).  Here a segment's 9 input rows are
+// fetched as 90 aligned float4 (columns [32 seg - 4, 32 seg + 36)), stored with 128-bit shared-memory stores, every
+// per-lane offset is a kernel-lifetime constant, K padding reads a zero word instead of a predicate, the epilogue
+// uses packed fp32x2 math and the output address is one base per segment plus constant per-lane offsets.
+__global__ void __launch_bounds__(128, 3) stem_mma_s2v_kernel(const StemParams p, int segs, long long total_tiles) {
+    constexpr int NC4 = 10, PITCH = 44, ZERO = 9 * PITCH, NLD = 3;
+    __shared__ __align__(16) float sin_all[4][9 * PITCH + 4];
+    __shared__ __align__(16) __nv_bfloat16 sout_all[4][16][64 + 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float* sin = sin_all[warp];
+    __nv_bfloat16 (*sout)[72] = sout_all[warp];
+    const int K = 9 * p.Cin, nrows = 3 * p.Cin;
+    for (int i = lane; i < 9 * PITCH + 4; i += 32) sin[i] = 0.f;          // rows of absent channels and the zero word
+
+    uint32_t bfrag[2][8][2];
+    float2 bias2[8];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = j * 8 + g, k0 = ks * 16 + 2 * t + 8 * h;
+                const float w0 = k0 < K ? p.w[n * K + k0] : 0.f, w1 = (k0 + 1) < K ? p.w[n * K + k0 + 1] : 0.f;
+                bfrag[ks][j][h] = pack_bf16x2(w0, w1);
+            }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        bias2[j] = make_float2(p.bias ? p.bias[j * 8 + 2 * t] : 0.f, p.bias ? p.bias[j * 8 + 2 * t + 1] : 0.f);
+    // shared-memory word of im2col element (pixel m, k): row (ci*3 + dy), column 2m + dx + 3
+    int ao[2][2][2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = ks * 16 + 2 * t + 8 * h + e;
+                if (k < K) {
+                    const int tap = k / p.Cin, ci = k % p.Cin, dy = tap / 3, dx = tap % 3;
+                    const int o = (ci * 3 + dy) * PITCH + dx + 3;
+                    ao[ks][h][e][0] = o + 2 * g; ao[ks][h][e][1] = o + 2 * (g + 8);
+                } else ao[ks][h][e][0] = ao[ks][h][e][1] = ZERO;
+            }
+    // gather constants of this lane's three float4 loads
+    int g_off[NLD], g_so[NLD], g_c4[NLD], g_dy[NLD];
+    bool g_ok[NLD];
+#pragma unroll
+    for (int q = 0; q < NLD; ++q) {
+        const int i = lane + 32 * q, row = i / NC4, c4 = i - row * NC4, ci = row / 3, dy = row - 3 * ci;
+        g_ok[q] = i < 9 * NC4 && row < nrows;
+        g_dy[q] = dy;
+        g_c4[q] = c4;
+        g_off[q] = ci * p.H * p.W + (dy - 1) * p.W + 4 * c4 - 4;
+        g_so[q] = row * PITCH + 4 * c4;
+    }
+    // output: constant element offset of this lane's four 16-byte stores relative to the segment's first pixel
+    const bool ph4 = p.y.layout == YRE_PHASE4;
+    const long long plane = (long long)p.y.B * p.y.Hp * p.y.Wp * p.y.C_total;
+    long long o_off[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = lane + 32 * q, px = i >> 3, c16 = i & 7;
+        o_off[q] = (ph4 ? (long long)(px & 1) * plane + (long long)(px >> 1) * p.y.C_total : (long long)px * p.y.C_total) + c16 * 8;
+    }
+
+    const int wstride = (int)gridDim.x * 4;
+    const int d_seg = wstride % segs, d_oy = (wstride / segs) % p.Ho, d_b = (wstride / segs) / p.Ho;
+    int tile = (int)blockIdx.x * 4 + warp;
+    int seg = tile % segs, oy = (tile / segs) % p.Ho, b = (tile / segs) / p.Ho;
+    const int ntiles = (int)total_tiles;
+    float4 pre[NLD];
+
+    auto fetch = [&](int fb, int foy, int fseg) {
+        const int iy0 = 2 * foy, ix0 = 32 * fseg;
+        const float* base = p.x + ((long long)fb * p.Cin * p.H + iy0) * p.W + ix0;
+#pragma unroll
+        for (int q = 0; q < NLD; ++q) {
+            const int x0 = ix0 - 4 + 4 * g_c4[q], iy = iy0 + g_dy[q] - 1;
+            const bool ok = g_ok[q] && iy >= 0 && iy < p.H && x0 >= 0 && x0 < p.W;   // outside = the conv's zero padding
+            pre[q] = ok ? __ldg(reinterpret_cast<const float4*>(base + g_off[q])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+
+    __syncwarp();
+    if (tile < ntiles) fetch(b, oy, seg);
+    for (; tile < ntiles; tile += wstride) {
+        const int ox0 = seg * SM_PX, cb = b, coy = oy;
+        __syncwarp();                                            // previous segment's smem readers are done
+#pragma unroll
+        for (int q = 0; q < NLD; ++q)
+            if (g_ok[q]) *reinterpret_cast<float4*>(sin + g_so[q]) = pre[q];
+        __syncwarp();
+        seg += d_seg; int cy = seg >= segs; seg -= cy ? segs : 0;
+        oy += d_oy + cy; cy = oy >= p.Ho; oy -= cy ? p.Ho : 0;
+        b += d_b + cy;
+        if (tile + wstride < ntiles) fetch(b, oy, seg);
+
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j][0] = bias2[j].x; acc[j][1] = bias2[j].y; acc[j][2] = bias2[j].x; acc[j][3] = bias2[j].y; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t a[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                a[2 * h + 0] = pack_bf16x2(sin[ao[ks][h][0][0]], sin[ao[ks][h][1][0]]);     // row g
+                a[2 * h + 1] = pack_bf16x2(sin[ao[ks][h][0][1]], sin[ao[ks][h][1][1]]);     // row g + 8
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_bf16_16816(acc[j], a, bfrag[ks][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float2 lo = make_float2(acc[j][0], acc[j][1]), hi = make_float2(acc[j][2], acc[j][3]);
+            if (p.act == YRE_ACT_SILU) {
+                const float2 hl = __fmul2_rn(lo, make_float2(0.5f, 0.5f)), hh = __fmul2_rn(hi, make_float2(0.5f, 0.5f));
+                float2 tl, th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tl.x) : "f"(hl.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tl.y) : "f"(hl.y));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(hh.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(hh.y));
+                lo = __ffma2_rn(hl, tl, hl); hi = __ffma2_rn(hh, th, hh);
+            }
+            *reinterpret_cast<uint32_t*>(&sout[g][j * 8 + 2 * t]) = pack_bf16x2(lo.x, lo.y);
+            *reinterpret_cast<uint32_t*>(&sout[g + 8][j * 8 + 2 * t]) = pack_bf16x2(hi.x, hi.y);
+        }
+        __syncwarp();
+        const long long ybase = ph4
+            ? ((((long long)((coy & 1) * 2) * p.y.B + cb) * p.y.Hp + (coy >> 1)) * p.y.Wp + (ox0 >> 1)) * p.y.C_total + p.y.c_off
+            : (((long long)cb * p.y.H + coy) * p.y.W + ox0) * p.y.C_total + p.y.c_off;
+        __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + ybase;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = lane + 32 * q, px = i >> 3, c16 = i & 7;
+            if (ox0 + px < p.Wo) *reinterpret_cast<uint4*>(yb + o_off[q]) = *reinterpret_cast<const uint4*>(&sout[px][c16 * 8]);
+        }
+    }
+}
+
 }  // namespace
 
 int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
@@ -273,7 +416,10 @@ int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long want = (tiles + 3) / 4;
         const unsigned grid = (unsigned)(want < (long long)sms * 4 ? want : (long long)sms * 4);
-        if (d.stride == 2) stem_mma_kernel<2><<<grid, 128, 0, s>>>(p, segs, tiles);
+        const bool vec = d.stride == 2 && d.W % 4 == 0 && (reinterpret_cast<uintptr_t>(d.x_nchw) & 15) == 0 &&
+                         (!getenv("YRE_STEM_VEC") || atoi(getenv("YRE_STEM_VEC")) != 0);
+        if (vec) stem_mma_s2v_kernel<<<grid, 128, 0, s>>>(p, segs, tiles);
+        else if (d.stride == 2) stem_mma_kernel<2><<<grid, 128, 0, s>>>(p, segs, tiles);
         else stem_mma_kernel<1><<<grid, 128, 0, s>>>(p, segs, tiles);
         YRE_LAUNCH_CHECK("stem_mma");
         return YRE_OK;
