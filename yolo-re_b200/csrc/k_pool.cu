@@ -161,6 +161,12 @@ __device__ __forceinline__ uint4 bf8_avg4(uint4 a, uint4 b, uint4 c, uint4 d) {
     r.w = bf2_quarter(bf2_add(bf2_add(bf2_add(a.w, b.w), c.w), d.w));
     return r;
 }
+__device__ __forceinline__ uint4 bf8_add(uint4 a, uint4 b) {
+    return make_uint4(bf2_add(a.x, b.x), bf2_add(a.y, b.y), bf2_add(a.z, b.z), bf2_add(a.w, b.w));
+}
+__device__ __forceinline__ uint4 bf8_quarter(uint4 a) {
+    return make_uint4(bf2_quarter(a.x), bf2_quarter(a.y), bf2_quarter(a.z), bf2_quarter(a.w));
+}
 __device__ __forceinline__ uint4 bf8_max(uint4 a, uint4 b) {
     return make_uint4(bf2_max(a.x, b.x), bf2_max(a.y, b.y), bf2_max(a.z, b.z), bf2_max(a.w, b.w));
 }
@@ -184,23 +190,46 @@ __global__ void __launch_bounds__(256, 3) adown_tiled_kernel(DView x, DView lo, 
     // (a load -> store -> load loop would serialise one HBM round trip per chunk)
     constexpr int NLDS = (AD_ROWS * AD_COLS * 8 + 255) / 256;       // 11
     uint4 buf[NLDS];
+    if (sizeof(T) == 2 && x.layout == YRE_NHWC) {
+        // row-linear addressing: thread (cc = tid/8, v = tid%8) reads column cc of all 10 rows (one pointer, a constant
+        // row stride), threads 0..159 the two extra columns -- no per-load div/mod or 64-bit index arithmetic
+        const int v = tid & 7, cc = tid >> 3;
+        const long long rs = (long long)x.W * x.C_total;
+        const T* col = xp + (((long long)b * x.H + iy0) * x.W + (ix0 + cc)) * x.C_total + x.c_off + c0 + v * 8;
+        const bool xin = (ix0 + cc) >= 0 && (ix0 + cc) < x.W;
 #pragma unroll
-    for (int q = 0; q < NLDS; ++q) {
-        const int i = tid + 256 * q;
-        const int v = i & 7, pix = i >> 3;
-        const int r = pix / AD_COLS, c = pix - r * AD_COLS;
-        const int iy = iy0 + r, ix = ix0 + c;
-        buf[q] = make_uint4(0u, 0u, 0u, 0u);
-        if (i < AD_ROWS * AD_COLS * 8 && iy >= 0 && iy < x.H && ix >= 0 && ix < x.W)
-            buf[q] = *reinterpret_cast<const uint4*>(xp + dview_pix(x, b, iy, ix) + c0 + v * (16 / (int)sizeof(T)));
-    }
+        for (int q = 0; q < AD_ROWS; ++q) {
+            const int iy = iy0 + q;
+            buf[q] = (xin && iy >= 0 && iy < x.H) ? *reinterpret_cast<const uint4*>(col + q * rs) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        const int er = tid >> 4, ec = AD_COLS - 2 + ((tid >> 3) & 1);
+        {
+            const int iy = iy0 + er, ix = ix0 + ec;
+            buf[AD_ROWS] = (tid < AD_ROWS * 16 && iy >= 0 && iy < x.H && ix >= 0 && ix < x.W)
+                ? *reinterpret_cast<const uint4*>(xp + (((long long)b * x.H + iy) * x.W + ix) * x.C_total + x.c_off + c0 + v * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
 #pragma unroll
-    for (int q = 0; q < NLDS; ++q) {
-        const int i = tid + 256 * q;
-        if (i < AD_ROWS * AD_COLS * 8) {
+        for (int q = 0; q < AD_ROWS; ++q) tile[q][cc][v] = buf[q];
+        if (tid < AD_ROWS * 16) tile[er][ec][v] = buf[AD_ROWS];
+    } else {
+#pragma unroll
+        for (int q = 0; q < NLDS; ++q) {
+            const int i = tid + 256 * q;
             const int v = i & 7, pix = i >> 3;
             const int r = pix / AD_COLS, c = pix - r * AD_COLS;
-            tile[r][c][v] = buf[q];
+            const int iy = iy0 + r, ix = ix0 + c;
+            buf[q] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < AD_ROWS * AD_COLS * 8 && iy >= 0 && iy < x.H && ix >= 0 && ix < x.W)
+                buf[q] = *reinterpret_cast<const uint4*>(xp + dview_pix(x, b, iy, ix) + c0 + v * (16 / (int)sizeof(T)));
+        }
+#pragma unroll
+        for (int q = 0; q < NLDS; ++q) {
+            const int i = tid + 256 * q;
+            if (i < AD_ROWS * AD_COLS * 8) {
+                const int v = i & 7, pix = i >> 3;
+                const int r = pix / AD_COLS, c = pix - r * AD_COLS;
+                tile[r][c][v] = buf[q];
+            }
         }
     }
     __syncthreads();
@@ -209,18 +238,35 @@ __global__ void __launch_bounds__(256, 3) adown_tiled_kernel(DView x, DView lo, 
         __nv_bfloat16* lop = reinterpret_cast<__nv_bfloat16*>(lo.ptr);
         __nv_bfloat16* hip = reinterpret_cast<__nv_bfloat16*>(hi.ptr);
         if (c0 < half) {
-            for (int i = tid; i < 2 * AD_TY * 2 * AD_TX * G; i += 256) {
-                const int g = i % G;
-                const int axl = (i / G) % (2 * AD_TX), ayl = i / (G * 2 * AD_TX);
-                const int ay = 2 * oy0 + ayl, ax = 2 * ox0 + axl;
-                const bool ok = ay < Ha && ax < Wa;
+            // item k of a thread = average pixel (ayl = k, axl = tid / 8), channel group g = tid % 8: the output address is
+            // one base per row parity plus a constant row stride
+            static_assert(G == 8 && 2 * AD_TX * G == 256, "item decomposition assumes 256 items per average row");
+            const int g = tid & 7, axl = tid >> 3;
+            const int ax = 2 * ox0 + axl;
+            const bool ph4 = lo.layout == YRE_PHASE4;
+            long long base[2], rstep;
+            if (ph4) {
+                for (int pk = 0; pk < 2; ++pk)
+                    base[pk] = (((((long long)(pk * 2 + (ax & 1)) * lo.B + b) * lo.Hp + oy0) * lo.Wp + (ax >> 1)) * lo.C_total) + lo.c_off + c0 + g * 8;
+                rstep = (long long)lo.Wp * lo.C_total;
+            } else {
+                base[0] = (((long long)b * lo.H + 2 * oy0) * lo.W + ax) * lo.C_total + lo.c_off + c0 + g * 8;
+                base[1] = base[0] + (long long)lo.W * lo.C_total;
+                rstep = 2ll * lo.W * lo.C_total;
+            }
+            const bool xok = ax < Wa, xst = ph4 ? (ax >> 1) < lo.Wp : xok;
+            // horizontal pair sums are shared by vertically adjacent averages: avg[k] = (h[k+1] + h[k+2]) / 4
+            uint4 hprev = bf8_add(tile[1][axl + 1][g], tile[1][axl + 2][g]);
+#pragma unroll
+            for (int k = 0; k < 2 * AD_TY; ++k) {
+                const int ay = 2 * oy0 + k;
+                const bool ok = xok && ay < Ha;
+                const uint4 hcur = bf8_add(tile[k + 2][axl + 1][g], tile[k + 2][axl + 2][g]);
                 uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (ok) o = bf8_avg4(tile[ayl + 1][axl + 1][g], tile[ayl + 1][axl + 2][g], tile[ayl + 2][axl + 1][g], tile[ayl + 2][axl + 2][g]);
-                if (lo.layout == YRE_PHASE4) {
-                    if ((ay >> 1) < lo.Hp && (ax >> 1) < lo.Wp) *reinterpret_cast<uint4*>(lop + dview_pix(lo, b, ay, ax) + c0 + g * 8) = o;
-                } else if (ok) {
-                    *reinterpret_cast<uint4*>(lop + dview_pix(lo, b, ay, ax) + c0 + g * 8) = o;
-                }
+                if (ok) o = bf8_quarter(bf8_add(hprev, hcur));
+                hprev = hcur;
+                const bool st = ph4 ? (xst && (ay >> 1) < lo.Hp) : ok;       // parity planes: cells without a source pixel hold zeros
+                if (st) *reinterpret_cast<uint4*>(lop + base[k & 1] + (k >> 1) * rstep) = o;
             }
         } else {
             for (int i = tid; i < AD_TY * AD_TX * G; i += 256) {

@@ -258,16 +258,18 @@ __global__ void __launch_bounds__(128, 3) stem_mma_kernel(const StemParams p, in
 // utilisation with only 12 resident warps per SM (ncu, profiles/r01_notes.md).  Here a segment's 9 input rows are
 // fetched as 90 aligned float4 (columns [32 seg - 4, 32 seg + 36)), stored with 128-bit shared-memory stores, every
 // per-lane offset is a kernel-lifetime constant, K padding reads a zero word instead of a predicate, the epilogue
-// uses packed fp32x2 math and the output address is one base per segment plus constant per-lane offsets.
-__global__ void __launch_bounds__(128, 3) stem_mma_s2v_kernel(const StemParams p, int segs, long long total_tiles) {
-    constexpr int NC4 = 10, PITCH = 44, ZERO = 9 * PITCH, NLD = 3;
-    __shared__ __align__(16) float sin_all[4][9 * PITCH + 4];
+// uses packed fp32x2 math and the output address is one base per segment plus constant per-lane offsets.  The
+// copies are cp.async (zero-fill = conv padding) into a per-warp ring of NST stages, NST-1 segments ahead.
+template <int NST, int MINB>
+__global__ void __launch_bounds__(128, MINB) stem_mma_s2v_kernel(const StemParams p, int segs, long long total_tiles) {
+    constexpr int NC4 = 10, PITCH = 44, ZERO = 9 * PITCH, STAGE = 9 * PITCH + 4, NLD = 3;
+    __shared__ __align__(16) float sin_all[4][NST * STAGE];                // per warp: ring of NST input stages
     __shared__ __align__(16) __nv_bfloat16 sout_all[4][16][64 + 8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     float* sin = sin_all[warp];
     __nv_bfloat16 (*sout)[72] = sout_all[warp];
     const int K = 9 * p.Cin, nrows = 3 * p.Cin;
-    for (int i = lane; i < 9 * PITCH + 4; i += 32) sin[i] = 0.f;          // rows of absent channels and the zero word
+    for (int i = lane; i < NST * STAGE; i += 32) sin[i] = 0.f;            // rows of absent channels and the zero words
 
     uint32_t bfrag[2][8][2];
     float2 bias2[8];
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(128, 3) stem_mma_s2v_kernel(const StemParams p
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         bias2[j] = make_float2(p.bias ? p.bias[j * 8 + 2 * t] : 0.f, p.bias ? p.bias[j * 8 + 2 * t + 1] : 0.f);
-    // shared-memory word of im2col element (pixel m, k): row (ci*3 + dy), column 2m + dx + 3
+    // word (inside a stage) of im2col element (pixel m, k): row (ci*3 + dy), column 2m + dx + 3; K padding -> zero word
     int ao[2][2][2][2];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
@@ -299,59 +301,70 @@ __global__ void __launch_bounds__(128, 3) stem_mma_s2v_kernel(const StemParams p
                     ao[ks][h][e][0] = o + 2 * g; ao[ks][h][e][1] = o + 2 * (g + 8);
                 } else ao[ks][h][e][0] = ao[ks][h][e][1] = ZERO;
             }
-    // gather constants of this lane's three float4 loads
-    int g_off[NLD], g_so[NLD], g_c4[NLD], g_dy[NLD];
+    // gather constants of this lane's three 16-byte copies
+    int g_off[NLD], g_c4[NLD], g_dy[NLD];
+    uint32_t g_so[NLD];
     bool g_ok[NLD];
+    const uint32_t sin_u32 = (uint32_t)__cvta_generic_to_shared(sin);
 #pragma unroll
     for (int q = 0; q < NLD; ++q) {
         const int i = lane + 32 * q, row = i / NC4, c4 = i - row * NC4, ci = row / 3, dy = row - 3 * ci;
         g_ok[q] = i < 9 * NC4 && row < nrows;
-        g_dy[q] = dy;
-        g_c4[q] = c4;
+        g_dy[q] = dy; g_c4[q] = c4;
         g_off[q] = ci * p.H * p.W + (dy - 1) * p.W + 4 * c4 - 4;
-        g_so[q] = row * PITCH + 4 * c4;
+        g_so[q] = sin_u32 + 4u * (uint32_t)(row * PITCH + 4 * c4);
     }
-    // output: constant element offset of this lane's four 16-byte stores relative to the segment's first pixel
     const bool ph4 = p.y.layout == YRE_PHASE4;
     const long long plane = (long long)p.y.B * p.y.Hp * p.y.Wp * p.y.C_total;
-    long long o_off[4];
+    int o_off[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int i = lane + 32 * q, px = i >> 3, c16 = i & 7;
-        o_off[q] = (ph4 ? (long long)(px & 1) * plane + (long long)(px >> 1) * p.y.C_total : (long long)px * p.y.C_total) + c16 * 8;
+        o_off[q] = (ph4 ? (px >> 1) : px) * p.y.C_total + c16 * 8;      // + plane for odd pixels of the parity layout
     }
 
+    // two cursors over this warp's segments: `f*` runs NST-1 segments ahead and issues the asynchronous copies
     const int wstride = (int)gridDim.x * 4;
     const int d_seg = wstride % segs, d_oy = (wstride / segs) % p.Ho, d_b = (wstride / segs) / p.Ho;
     int tile = (int)blockIdx.x * 4 + warp;
     int seg = tile % segs, oy = (tile / segs) % p.Ho, b = (tile / segs) / p.Ho;
+    int ftile = tile, fseg = seg, foy = oy, fb = b, fstage = 0, cstage = 0;
     const int ntiles = (int)total_tiles;
-    float4 pre[NLD];
 
-    auto fetch = [&](int fb, int foy, int fseg) {
-        const int iy0 = 2 * foy, ix0 = 32 * fseg;
-        const float* base = p.x + ((long long)fb * p.Cin * p.H + iy0) * p.W + ix0;
+    auto issue = [&]() {           // cp.async the segment under the f-cursor into stage fstage (zero-fill = conv padding), advance
+        if (ftile < ntiles) {
+            const int iy0 = 2 * foy, ix0 = 32 * fseg;
+            const float* base = p.x + ((long long)fb * p.Cin * p.H + iy0) * p.W + ix0;
 #pragma unroll
-        for (int q = 0; q < NLD; ++q) {
-            const int x0 = ix0 - 4 + 4 * g_c4[q], iy = iy0 + g_dy[q] - 1;
-            const bool ok = g_ok[q] && iy >= 0 && iy < p.H && x0 >= 0 && x0 < p.W;   // outside = the conv's zero padding
-            pre[q] = ok ? __ldg(reinterpret_cast<const float4*>(base + g_off[q])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < NLD; ++q) {
+                const int x0 = ix0 - 4 + 4 * g_c4[q], iy = iy0 + g_dy[q] - 1;
+                const bool in = iy >= 0 && iy < p.H && x0 >= 0 && x0 < p.W;
+                if (g_ok[q]) {
+                    const float* src = in ? base + g_off[q] : p.x;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(g_so[q] + 4u * (uint32_t)(fstage * STAGE)), "l"(src), "r"(in ? 16 : 0) : "memory");
+                }
+            }
+            fseg += d_seg; int cy = fseg >= segs; fseg -= cy ? segs : 0;
+            foy += d_oy + cy; cy = foy >= p.Ho; foy -= cy ? p.Ho : 0;
+            fb += d_b + cy;
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        ftile += wstride;
+        if (++fstage == NST) fstage = 0;
     };
 
     __syncwarp();
-    if (tile < ntiles) fetch(b, oy, seg);
+#pragma unroll
+    for (int i = 0; i < NST - 1; ++i) issue();
     for (; tile < ntiles; tile += wstride) {
         const int ox0 = seg * SM_PX, cb = b, coy = oy;
-        __syncwarp();                                            // previous segment's smem readers are done
-#pragma unroll
-        for (int q = 0; q < NLD; ++q)
-            if (g_ok[q]) *reinterpret_cast<float4*>(sin + g_so[q]) = pre[q];
+        issue();                                                  // refills the stage the previous iteration read
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
         __syncwarp();
+        const float* st = sin + cstage * STAGE;
         seg += d_seg; int cy = seg >= segs; seg -= cy ? segs : 0;
         oy += d_oy + cy; cy = oy >= p.Ho; oy -= cy ? p.Ho : 0;
         b += d_b + cy;
-        if (tile + wstride < ntiles) fetch(b, oy, seg);
 
         float acc[8][4];
 #pragma unroll
@@ -361,8 +374,8 @@ __global__ void __launch_bounds__(128, 3) stem_mma_s2v_kernel(const StemParams p
             uint32_t a[4];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                a[2 * h + 0] = pack_bf16x2(sin[ao[ks][h][0][0]], sin[ao[ks][h][1][0]]);     // row g
-                a[2 * h + 1] = pack_bf16x2(sin[ao[ks][h][0][1]], sin[ao[ks][h][1][1]]);     // row g + 8
+                a[2 * h + 0] = pack_bf16x2(st[ao[ks][h][0][0]], st[ao[ks][h][1][0]]);     // row g
+                a[2 * h + 1] = pack_bf16x2(st[ao[ks][h][0][1]], st[ao[ks][h][1][1]]);     // row g + 8
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) mma_bf16_16816(acc[j], a, bfrag[ks][j]);
@@ -382,7 +395,7 @@ __global__ void __launch_bounds__(128, 3) stem_mma_s2v_kernel(const StemParams p
             *reinterpret_cast<uint32_t*>(&sout[g][j * 8 + 2 * t]) = pack_bf16x2(lo.x, lo.y);
             *reinterpret_cast<uint32_t*>(&sout[g + 8][j * 8 + 2 * t]) = pack_bf16x2(hi.x, hi.y);
         }
-        __syncwarp();
+        __syncwarp();                                             // sout complete; all lanes are done reading stage cstage
         const long long ybase = ph4
             ? ((((long long)((coy & 1) * 2) * p.y.B + cb) * p.y.Hp + (coy >> 1)) * p.y.Wp + (ox0 >> 1)) * p.y.C_total + p.y.c_off
             : (((long long)cb * p.y.H + coy) * p.y.W + ox0) * p.y.C_total + p.y.c_off;
@@ -390,9 +403,12 @@ __global__ void __launch_bounds__(128, 3) stem_mma_s2v_kernel(const StemParams p
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int i = lane + 32 * q, px = i >> 3, c16 = i & 7;
-            if (ox0 + px < p.Wo) *reinterpret_cast<uint4*>(yb + o_off[q]) = *reinterpret_cast<const uint4*>(&sout[px][c16 * 8]);
+            if (ox0 + px < p.Wo)
+                *reinterpret_cast<uint4*>(yb + o_off[q] + ((ph4 && (px & 1)) ? plane : 0ll)) = *reinterpret_cast<const uint4*>(&sout[px][c16 * 8]);
         }
+        if (++cstage == NST) cstage = 0;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 }  // namespace
@@ -418,7 +434,7 @@ int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
         const unsigned grid = (unsigned)(want < (long long)sms * 4 ? want : (long long)sms * 4);
         const bool vec = d.stride == 2 && d.W % 4 == 0 && (reinterpret_cast<uintptr_t>(d.x_nchw) & 15) == 0 &&
                          (!getenv("YRE_STEM_VEC") || atoi(getenv("YRE_STEM_VEC")) != 0);
-        if (vec) stem_mma_s2v_kernel<<<grid, 128, 0, s>>>(p, segs, tiles);
+        if (vec) stem_mma_s2v_kernel<3, 3><<<grid, 128, 0, s>>>(p, segs, tiles);   // 4 stages or 4 CTAs/SM (128 regs, spills) measured no better
         else if (d.stride == 2) stem_mma_kernel<2><<<grid, 128, 0, s>>>(p, segs, tiles);
         else stem_mma_kernel<1><<<grid, 128, 0, s>>>(p, segs, tiles);
         YRE_LAUNCH_CHECK("stem_mma");
