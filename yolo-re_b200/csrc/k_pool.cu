@@ -274,25 +274,31 @@ __global__ void __launch_bounds__(256, 3) adown_tiled_kernel(DView x, DView lo, 
                 const int oxl = (i / G) % AD_TX, oyl = i / (G * AD_TX);
                 const int oy = oy0 + oyl, ox = ox0 + oxl;
                 if (oy >= hi.H || ox >= hi.W) continue;
+                // max over the 3x3 window of 2x2 averages: horizontal pair sums h[r][q] are shared by the two average rows
+                // that use them, and the exact x0.25 is applied once after the max (monotonic, power of two)
                 uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);      // -inf pairs
-                uint4 prev[4], cur[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) prev[q] = tile[2 * oyl][2 * oxl + q][g];
+                uint4 hp[3], hc[3];
+                {
+                    const uint4 t0 = tile[2 * oyl][2 * oxl][g], t1 = tile[2 * oyl][2 * oxl + 1][g], t2 = tile[2 * oyl][2 * oxl + 2][g], t3 = tile[2 * oyl][2 * oxl + 3][g];
+                    hp[0] = bf8_add(t0, t1); hp[1] = bf8_add(t1, t2); hp[2] = bf8_add(t2, t3);
+                }
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) cur[q] = tile[2 * oyl + j + 1][2 * oxl + q][g];
+                    const uint4 t0 = tile[2 * oyl + j + 1][2 * oxl][g], t1 = tile[2 * oyl + j + 1][2 * oxl + 1][g],
+                                t2 = tile[2 * oyl + j + 1][2 * oxl + 2][g], t3 = tile[2 * oyl + j + 1][2 * oxl + 3][g];
+                    hc[0] = bf8_add(t0, t1); hc[1] = bf8_add(t1, t2); hc[2] = bf8_add(t2, t3);
                     const int ay = 2 * oy - 1 + j;
                     if (ay >= 0 && ay < Ha) {
 #pragma unroll
                         for (int q = 0; q < 3; ++q) {
                             const int ax = 2 * ox - 1 + q;
-                            if (ax >= 0 && ax < Wa) m = bf8_max(m, bf8_avg4(prev[q], prev[q + 1], cur[q], cur[q + 1]));
+                            if (ax >= 0 && ax < Wa) m = bf8_max(m, bf8_add(hp[q], hc[q]));
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) prev[q] = cur[q];
+                    for (int q = 0; q < 3; ++q) hp[q] = hc[q];
                 }
+                m = bf8_quarter(m);
                 *reinterpret_cast<uint4*>(hip + dview_pix(hi, b, oy, ox) + (c0 - half) + g * 8) = m;
             }
         }
