@@ -51,7 +51,7 @@ def test_fp32_end_to_end_vs_reference_fixture(name, fix, request):
         assert np.abs(r[:, :, ::s, ::s].cpu().numpy() - gd[f"raw{i}_sub"]).max() <= 2e-3
 
 
-@pytest.mark.parametrize("size,batch", [(320, 1), (416, 2), (640, 1), (256, 4)])
+@pytest.mark.parametrize("size,batch", [(320, 1), (416, 2), (640, 1), (256, 4), (1280, 1)])
 def test_fp32_end_to_end_vs_oracle_and_nms(gelan_c, size, batch):
     """Input sizes 320/416/640 and batch 1/2/4 (reference tests/test_model.py:80-95), numerics vs the
     oracle, then NMS through the public API bit-exact vs the oracle NMS on the SAME predictions."""
@@ -119,6 +119,23 @@ def test_bf16_end_to_end_drift_reported(gelan_c):
     ref = N.non_max_suppression(y.permute(0, 2, 1).contiguous().cpu(), 0.25, 0.45)
     for a, b in zip(dets, ref):
         assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_config5_1280_eval_regime_nms_bit_exact(gelan_c):
+    """BASELINE.json config 5: 1280x1280 (33 600 anchors/image), eval-time NMS thresholds conf 0.001 / iou 0.6,
+    max_det 300 -- the bf16 product path end to end, then NMS bit-exact vs the oracle on the SAME predictions."""
+    nodes, nc, sd = gelan_c
+    x = G.fractal(2, 1280, torch.Generator().manual_seed(13))
+    m = build("gelan-c", sd, "bf16")
+    y, raws = m(x.to(DEV))
+    assert y.shape == (2, 84, 33600) and [tuple(r.shape[2:]) for r in raws] == [(160, 160), (80, 80), (40, 40)]
+    pred = y.permute(0, 2, 1).contiguous()
+    n_cand = (pred[:, :, 4:].max(2).values > 0.001).sum(1)
+    assert int(n_cand.min()) > 20000                                  # the stress regime: (almost) every anchor is a candidate
+    dets = yolo_b200.non_max_suppression(pred, 0.001, 0.6, max_det=300)
+    ref = N.non_max_suppression(pred.cpu(), 0.001, 0.6, max_det=300)
+    for a, b in zip(dets, ref):
+        assert a.shape[0] == 300 and np.array_equal(a.cpu().numpy(), b)
 
 
 def test_yolov9c_dual_head_outputs(yolov9_c):
