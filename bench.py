@@ -181,6 +181,7 @@ def main():
     model = model.to(dev).eval().set_precision(args.precision)
     model.check_weights = False
     model.fresh_outputs = False
+    model.use_cuda_graph = os.environ.get("YRE_BENCH_GRAPH", "1") != "0"     # static buffers -> the forward replays as one CUDA graph
 
     Bn = args.batch
     x_host = make_inputs(Bn, seed=7 + rank).pin_memory()

@@ -113,6 +113,7 @@ class YOLO(nn.Module):
         self.precision = "bf16"          # "bf16" (tcgen05) | "fp32" (FFMA validation mode)
         self.fresh_outputs = True        # False: return the plan's static output buffers (no allocation)
         self.check_weights = True        # re-fold when a parameter was modified in place
+        self.use_cuda_graph = False      # with fresh_outputs=False: capture the launch list once per input buffer and replay it
         self.main_only = False           # dual-head models: True compiles the main branch only -> (y, raws) like a single head
         self._plans: dict = {}
         self.register_load_state_dict_post_hook(lambda m, _k: m.invalidate())
