@@ -188,6 +188,8 @@ typedef struct yre_letterbox_desc {
  * reference returns go to the optional outputs.  Fails with YRE_EINVAL when the padded size is not S x S. */
 int yre_letterbox_geometry(yre_letterbox_desc* d, double* ratio, int32_t* pad_w, int32_t* pad_h);
 int yre_letterbox_u8(const yre_letterbox_desc* d, yre_stream_t s);
+/* n images sharing new_shape and out_mode in as few launches as possible (32 images per launch) */
+int yre_letterbox_u8_batch(const yre_letterbox_desc* d, int32_t n, yre_stream_t s);
 /* K9 replaces scale_boxes                                scripts/detect.py:74-109
  * boxes: n rows of xyxy fp32, `row_stride` floats apart (6 for detection rows), updated in place:
  * x = clamp((x - pad_w) / gain, 0, orig_w), y likewise -- fp32, true division, as torch does on the CPU. */

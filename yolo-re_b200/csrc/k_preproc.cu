@@ -39,8 +39,12 @@ __device__ __forceinline__ void lb_coeff(int d, double scale, int sn, bool clamp
     a1 = __float2int_rn(__fmul_rn(f, 2048.f));
 }
 
+constexpr int LB_BATCH = 32;                  // images per launch (descriptors travel as kernel parameters, < 4 KB)
+struct LbBatch { LbParams p[LB_BATCH]; };
+
 template <int OUT_U8>
-__global__ void __launch_bounds__(256) letterbox_kernel(const LbParams p) {
+__global__ void __launch_bounds__(256) letterbox_kernel(const __grid_constant__ LbBatch batch) {
+    const LbParams& p = batch.p[blockIdx.z];
     const int X = blockIdx.x * 32 + (threadIdx.x & 31), Y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (X >= p.S || Y >= p.S) return;
     int v0 = p.c0, v1 = p.c1, v2 = p.c2;
@@ -115,25 +119,44 @@ extern "C" int yre_letterbox_geometry(yre_letterbox_desc* d, double* ratio, int3
     return YRE_OK;
 }
 
-extern "C" int yre_letterbox_u8(const yre_letterbox_desc* d, yre_stream_t s) {
+static int lb_fill(const yre_letterbox_desc* d, LbParams& p) {
     if (!d || !d->src || !d->dst) YRE_FAIL(YRE_EINVAL, "letterbox: null pointer");
     if (d->h <= 0 || d->w <= 0 || d->row_pitch < 3ll * d->w) YRE_FAIL(YRE_EINVAL, "letterbox: bad source extent");
     if (d->new_w <= 0 || d->new_h <= 0 || d->top < 0 || d->left < 0 || d->left + d->new_w > d->new_shape || d->top + d->new_h > d->new_shape)
         YRE_FAIL(YRE_EINVAL, "letterbox: geometry does not fit %d", d->new_shape);
     if (d->out_mode != YRE_LB_F32_CHW && d->out_mode != YRE_LB_U8_HWC) YRE_FAIL(YRE_EINVAL, "letterbox: bad out_mode");
-    LbParams p;
     p.src = d->src; p.h = d->h; p.w = d->w; p.pitch = d->row_pitch; p.S = d->new_shape;
     p.nw = d->new_w; p.nh = d->new_h; p.top = d->top; p.left = d->left;
     p.c0 = d->color[0]; p.c1 = d->color[1]; p.c2 = d->color[2];
     p.mode = (d->w == d->new_w && d->h == d->new_h) ? 1 : ((d->w == 2 * d->new_w && d->h == 2 * d->new_h) ? 2 : 0);
     p.sx = (double)d->w / d->new_w; p.sy = (double)d->h / d->new_h;
     p.dst = d->dst;
-    dim3 grid(yre_cdiv(p.S, 32), yre_cdiv(p.S, 8));
-    if (d->out_mode == YRE_LB_U8_HWC) letterbox_kernel<1><<<grid, 256, 0, (cudaStream_t)s>>>(p);
-    else letterbox_kernel<0><<<grid, 256, 0, (cudaStream_t)s>>>(p);
-    YRE_LAUNCH_CHECK("letterbox");
     return YRE_OK;
 }
+
+// n images with the same new_shape and out_mode, up to LB_BATCH per launch (grid.z = image)
+extern "C" int yre_letterbox_u8_batch(const yre_letterbox_desc* d, int32_t n, yre_stream_t s) {
+    if (n < 0 || (n > 0 && !d)) YRE_FAIL(YRE_EINVAL, "letterbox: bad batch");
+    for (int i0 = 0; i0 < n; i0 += LB_BATCH) {
+        const int m = n - i0 < LB_BATCH ? n - i0 : LB_BATCH;
+        LbBatch b;
+        for (int i = 0; i < m; ++i) {
+            if (d[i0 + i].new_shape != d[0].new_shape || d[i0 + i].out_mode != d[0].out_mode)
+                YRE_FAIL(YRE_EINVAL, "letterbox: a batch must share new_shape and out_mode");
+            const int rc = lb_fill(&d[i0 + i], b.p[i]);
+            if (rc) return rc;
+        }
+        for (int i = m; i < LB_BATCH; ++i) b.p[i] = b.p[0];
+        const int S = d[0].new_shape;
+        dim3 grid(yre_cdiv(S, 32), yre_cdiv(S, 8), (unsigned)m);
+        if (d[0].out_mode == YRE_LB_U8_HWC) letterbox_kernel<1><<<grid, 256, 0, (cudaStream_t)s>>>(b);
+        else letterbox_kernel<0><<<grid, 256, 0, (cudaStream_t)s>>>(b);
+        YRE_LAUNCH_CHECK("letterbox");
+    }
+    return YRE_OK;
+}
+
+extern "C" int yre_letterbox_u8(const yre_letterbox_desc* d, yre_stream_t s) { return yre_letterbox_u8_batch(d, 1, s); }
 
 extern "C" int yre_scale_boxes(float* boxes, int32_t n, int32_t row_stride, float pad_w, float pad_h, float gain,
                                float orig_w, float orig_h, yre_stream_t s) {

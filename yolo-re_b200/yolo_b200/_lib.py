@@ -71,6 +71,7 @@ SYMBOLS = {
     "yre_nms_batched": (C.c_int, [C.POINTER(NmsDesc), C.c_void_p]),
     "yre_letterbox_geometry": (C.c_int, [C.POINTER(LetterboxDesc), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "yre_letterbox_u8": (C.c_int, [C.POINTER(LetterboxDesc), C.c_void_p]),
+    "yre_letterbox_u8_batch": (C.c_int, [C.POINTER(LetterboxDesc), C.c_int32, C.c_void_p]),
     "yre_scale_boxes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "yre_plan_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "yre_plan_destroy": (None, [C.c_void_p]),

@@ -72,11 +72,13 @@ def preprocess(imgs, new_shape: int = 640, color: tuple[int, int, int] = (114, 1
     if tuple(out.shape) != (len(srcs), 3, new_shape, new_shape) or out.dtype != torch.float32 or not out.is_contiguous() or not out.is_cuda:
         raise ValueError("preprocess: `out` must be a contiguous CUDA fp32 [B, 3, S, S] tensor")
     ratios, pads = [], []
+    descs = (L.LetterboxDesc * len(srcs))()
     for i, src in enumerate(srcs):
         d, r, pad = _desc(src, new_shape, color)
         d.out_mode, d.dst = L.LB_F32_CHW, out[i].data_ptr()
-        L.check(L.lib().yre_letterbox_u8(C.byref(d), _stream()), "letterbox_u8")
+        descs[i] = d
         ratios.append((r, r)); pads.append(pad)
+    L.check(L.lib().yre_letterbox_u8_batch(descs, len(srcs), _stream()), "letterbox_u8_batch")
     return out, ratios, pads
 
 
