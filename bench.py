@@ -165,6 +165,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus, all_cpus = None, os.sched_getaffinity(0)
+    if os.environ.get("YRE_BENCH_NUMA", "1") != "0":
+        from yolo_b200.shard import bind_to_gpu_numa_node
+        numa_cpus = bind_to_gpu_numa_node(local)       # before any pinned allocation
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -405,6 +409,7 @@ def main():
     # ---- CPU baseline: oracle port on the host cores, bounded sample ----
     cpu = None
     if not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)                  # the CPU arm gets every host core again
         torch.set_num_threads(os.cpu_count() or 1)
         xs = x_host[:2].clone()
         cpu_reference_step(nodes, nc, sd, xs)
@@ -424,6 +429,7 @@ def main():
                    "per_gpu_batch": Bn, "global_batch": Bn * world, "l2": "input batch (315 MB) and activations exceed the 126 MB L2",
                    "detections_per_image": dets_per_img, "parallelism": f"image-sharded x{world}, no data-path collective"},
         "e2e_u8_input": e2e_u8,
+        "host_cores_bound": (len(numa_cpus) if numa_cpus else None),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "how": "pinned host fp32 batch -> H2D (copy stream, double-buffered) -> YOLO.forward -> nms -> D2H detections"},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,

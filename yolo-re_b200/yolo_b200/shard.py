@@ -27,3 +27,30 @@ def aggregate_throughput(n_images_local: int, elapsed_s_local: float, device=Non
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total, tmax = int(n.item()), float(t.item())
     return (total / tmax if tmax > 0 else 0.0), total, tmax
+
+
+def bind_to_gpu_numa_node(device_index: int) -> list[int] | None:
+    """One process per GPU: restrict this process to the CPU cores NVML reports as local to the GPU, so pinned host
+    buffers allocated afterwards are first-touched on the GPU's NUMA node and the per-step H2D copy does not cross the
+    socket interconnect.  Returns the core list, or None when NVML / affinity is unavailable (never raises)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        handle = None
+        try:
+            bus = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in range(ncpu) if (int(words[c // 64]) >> (c % 64)) & 1 and c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
