@@ -392,8 +392,22 @@ def main():
     cf = fam[conv_name]
     achieved = cf["flops"] / (cf["ms"] / 1e3) / 1e12 if cf["ms"] > 0 else 0.0
     all_conv_flops = sum(f["flops"] for n, f in fam.items() if n.startswith("conv") or n == "stem")
+    # DRAM bytes of the conv launches of one step, from the committed ncu launch list of this same command
+    # (profiles/*_ncu_launch_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum per kernel family)
+    traffic, traffic_src = None, None
+    try:
+        import csv
+        summ = sorted((ROOT / "profiles").glob("r*_ncu_launch_summary.csv"))
+        if summ and Bn == PER_GPU_BATCH:
+            rows = [r for r in csv.DictReader(open(summ[-1])) if r["kernel"].startswith("conv")]
+            traffic = sum(float(r["dram_read_MB"]) + float(r["dram_write_MB"]) for r in rows) * 1e6
+            traffic_src = f"{summ[-1].name}: {sum(int(r['launches_per_step']) for r in rows)} conv launches of one step"
+    except Exception:
+        traffic, traffic_src = None, None
     roofline = {"bound": "tensor", "kernel": conv_name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                "frac": achieved / peak_tf, "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
+                "traffic_unit": "bytes per step (all conv launches; algorithmic unfused bf16 bytes = 2(|in|+|out|+|w|) = 28.9e9)",
+                "traffic_source": traffic_src,
                 "launches_per_step": cf["launches"], "ms_per_step": cf["ms"], "flops_per_step": cf["flops"],
                 "timing": f"per-launch CUDA-event intervals minus the measured event-record gap ({gap_ms * 1e3:.1f} us/interval); "
                           f"all ops: raw {raw_sum:.3f} ms, un-instrumented pass {plain_ms:.3f} ms",

@@ -1,34 +1,34 @@
-// K1 (product engine): implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 / TMEM),
-// operands staged by TMA, fused epilogue.
+// K1 (product engine): convolutions on the 5th-gen tensor cores (tcgen05 / TMEM), operands staged by TMA, fused epilogue.
 //
 //   y = [res +] act(conv(x, w) + bias)      reference: src/yolo/blocks/conv.py:88-89 (+ conv.py:140-141,
 //                                           bottleneck.py:49-51, heads/detect.py:52,61, auxiliary.py:61-62)
 //
 // GEMM view      D[M x N] = A[M x K] * W[N x K]^T,  M = output pixels, N = Cout, K = taps * Cin.
-// A tile         128 output pixels = a (tb images) x (th rows) x (tw cols) patch; for filter tap
-//                (dy,dx) and channel chunk kc ONE TMA box {BLOCK_K ch, tw, th, tb} shifted by the tap
-//                offset is loaded straight from the NHWC activation -- out-of-bounds coordinates are
-//                zero-filled by the TMA unit, which *is* the conv padding (no im2col buffer, no halo).
-//                Stride-2 convs read a parity-plane (YRE_PHASE4) input, so each tap is again a
-//                unit-stride box (5-D tensor map, plane index = tap parity).
-// W tile         {BLOCK_K, BLOCK_N} box of the K-major [Cout][taps*Cin] weight matrix.
-// Both land in 128B- (BLOCK_K=64) or 64B- (BLOCK_K=32) swizzled shared memory that the UMMA smem
-// descriptors read directly.  Accumulators live in TMEM (2 x 256 columns, double-buffered), so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+// Three kernels share the PTX wrappers, the epilogue and the host-side plan (ConvTcPlan):
+//   conv_tc_kernel            generic implicit GEMM: for filter tap (dy,dx) and channel chunk kc ONE TMA box
+//                             {BLOCK_K ch, tw, th, tb} shifted by the tap offset is loaded straight from the NHWC
+//                             activation -- out-of-bounds coordinates are zero-filled by the TMA unit, which *is* the
+//                             conv padding (no im2col buffer).  Stride-2 convs read a parity-plane (YRE_PHASE4) input,
+//                             so each tap is again a unit-stride box (5-D tensor map, plane index = tap parity).
+//   conv3_halo_kernel         3x3 stride-1, Cin <= 64, Cout 32/64: weights resident in shared memory, one 10x18-pixel
+//                             halo box per 8x16 patch, the nine taps are descriptor shifts of that one tile.
+//   conv3_halo_stream_kernel  3x3 stride-1, Cin a multiple of 64: same halo tile per 64-channel chunk, weight boxes
+//                             streamed through a second ring, optionally two patches per weight box.
+// Operands land in 128B- (BLOCK_K=64) or 64B- (BLOCK_K=32) swizzled shared memory that the UMMA smem descriptors read
+// directly.  Accumulators live in a ring of TMEM buffers (6x64, 4x128, 3x160 or 2x256 columns), so the epilogue of
+// one tile overlaps the MMAs of the next ones.  All kernels are persistent (grid = min(work units, SMs)).
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over a static tile schedule):
-//   warp 0 : TMA producer          warp 1 : tcgen05.mma issuer       warp 2 : TMEM alloc / dealloc
-//   warps 4..15 : epilogue, three groups of four warps; a group takes every third tile of the CTA (its
-//   accumulator sits in one of up to 4 TMEM buffers), warp w owns TMEM lane quarter w%4 (32 pixels), with its
-//   own double-buffered staging tile and its own TMA stores -- no CTA-wide barrier.  The epilogue is
-//   MUFU-bound (one tanh per output, 16 MUFU lanes per SM), so three warps per scheduler keep that pipe
-//   busy while their siblings wait on TMEM loads / staging / stores.
-// Epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> 128B-swizzled shared-memory staging
-// tile -> TMA store (cp.async.bulk.tensor) into the consumer's channel window (concat-slice write,
-// ragged tile edges clipped by the TMA unit).  fp32 outputs (the raw head logits) use direct 16-byte
-// stores.  All role loops are warp-uniform (elect.sync picks the issuing lane), which keeps the
-// descriptors in uniform registers -- a lane-0 branch made ptxas wrap every UTCHMMA/UTMALDG in a
-// serialising ELECT loop (profiles/r01_notes.md).
+// Warp roles of the generic kernel (384 or 512 threads, 1 CTA / SM):
+//   warps 0 / 2 : TMA producers, warps 1 / 3 : tcgen05.mma issuers (two producer-issuer pairs ping-pong over the CTA's
+//   tiles when the stage ring is deep enough), warp 2 also allocates TMEM;
+//   warps 4..   : epilogue, two or three groups of four warps (warp w owns TMEM lane quarter w % 4 = 32 pixels); groups
+//   take tiles round-robin and/or split the 32-column chunks of a tile, each warp has its own double-buffered staging
+//   tile and issues its own TMA stores -- no CTA-wide barrier in the steady state.
+// Epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> 64B-swizzled shared-memory staging tile -> TMA store
+// (cp.async.bulk.tensor) into the consumer's channel window (concat-slice write, ragged tile edges clipped by the TMA
+// unit).  fp32 outputs (the raw head logits) use direct 16-byte stores.  All role loops are warp-uniform (elect.sync
+// picks the issuing lane), which keeps the descriptors in uniform registers -- a lane-0 branch made ptxas wrap every
+// UTCHMMA/UTMALDG in a serialising ELECT loop.  Measurements behind the design choices: profiles/r01_notes.md.
 #include "yre_common.cuh"
 #include <cuda.h>
 #include <cstring>

@@ -2,10 +2,14 @@
 //
 //   y = act(conv(x, w) + bias)          -- reference: layers.stem1, src/yolo/blocks/conv.py:88-89
 //
-// HBM-bound (AI ~ 23 FLOP/B): one thread owns 4 consecutive output pixels of a row, keeps their
-// 3 x (4*stride+1) x Cin input patch in registers, and walks the output channels 16 at a time with
-// the folded weights broadcast from shared memory (one weight read feeds 4 pixels).  Output is written channels-last (optionally as the 4 parity planes the
-// stride-2 tcgen05 conv that follows wants), 32 B per store.
+// HBM-bound by nature (AI ~ 23 FLOP/B); output is written channels-last, optionally as the 4 parity planes the
+// stride-2 tcgen05 conv that follows wants.  Three kernels:
+//   stem_kernel           fp32 FMA (validation mode, any Cin <= 4 / Cout): one thread owns 4 consecutive output pixels,
+//                         keeps their input patch in registers and walks the output channels 16 at a time with the
+//                         folded weights broadcast from shared memory.
+//   stem_mma_kernel       bf16 product path, mma.sync m16n8k16 with K = 9*Cin padded to 32 (too thin for tcgen05),
+//                         scalar gather; used for stride 1 or W % 4 != 0.
+//   stem_mma_s2v_kernel   the stride-2 product kernel: vectorised cp.async gather ring (see its comment).
 #include "yre_common.cuh"
 #include <cstdlib>
 
