@@ -248,7 +248,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
 // `sbias` = shared-memory copy of the bias vector (whole Cout); packed fp32x2 ops (FADD2/FMUL2/FFMA2) halve
 // the FP issue slots, SiLU costs one MUFU.TANH per element.
 template <int NC>
-__device__ __forceinline__ void epilogue_math(const TcParams& p, const float* sbias, const uint32_t* v, float* f, bool valid, long long pix, int n) {
+__device__ __forceinline__ void epilogue_math(const TcParams& p, const float* sbias, const uint32_t* v, float* f, bool valid, long long pix, int n,
+                                              const uint4* rpre = nullptr) {
     float2 x2[NC / 2];
 #pragma unroll
     for (int i = 0; i < NC; i += 4) {
@@ -280,7 +281,7 @@ __device__ __forceinline__ void epilogue_math(const TcParams& p, const float* sb
             const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ctot + p.res_coff + n;
 #pragma unroll
             for (int i = 0; i < NC; i += 8) {
-                const uint4 u = *reinterpret_cast<const uint4*>(r + i);
+                const uint4 u = rpre ? rpre[i / 8] : *reinterpret_cast<const uint4*>(r + i);     // rpre: loaded a chunk ahead
                 f[i + 0] += __uint_as_float(u.x << 16); f[i + 1] += __uint_as_float(u.x & 0xffff0000u);
                 f[i + 2] += __uint_as_float(u.y << 16); f[i + 3] += __uint_as_float(u.y & 0xffff0000u);
                 f[i + 4] += __uint_as_float(u.z << 16); f[i + 5] += __uint_as_float(u.z & 0xffff0000u);
@@ -325,6 +326,9 @@ __device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base
 // warpgroup grp = (tg, cs): tile-group tg takes local tiles tg, tg+GT, ...; inside a tile the csplit warpgroups of
 // a tile-group share the 32-column chunks round-robin.  tfull0 / tempty0 = addresses of the first accumulator
 // full / empty mbarrier (8 bytes apart per buffer).
+// PF: prefetch the next chunk's tcgen05.ld into a second 32-register buffer (the 168-register / 384-thread kernels); the
+// 512-thread kernels have 128 registers per thread and at most two chunks per tile, so they load each chunk in place.
+template <bool PF>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* tmY, const float* sbias, int warp, int lane,
                                               uint32_t tmem_base, uint32_t out_base, uint32_t tfull0, uint32_t tempty0) {
         // ================= epilogue (warp-local, no CTA barrier) =================
@@ -364,6 +368,15 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
             const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
             const uint32_t tfull = tfull0 + 8u * acc, tempty = tempty0 + 8u * acc;
+            // bf16 residual of the chunk about to be processed: fetched before the accumulator wait / one chunk ahead,
+            // so its global-memory latency hides behind the MMAs and the previous chunk's staging (it was the top stall)
+            const bool res16 = p.res && !p.res_f32 && valid;
+            const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ctot + p.res_coff + n0;
+            uint4 rr[4];
+            if (res16 && cs * 32 + 32 <= p.block_n) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + cs * 32 + 8 * i);
+            }
             if (tracer) trace(p.dbg, 2, tn, 20);
             mbar_wait(tfull, acc_phase, p.dbg, 4);
             tc_fence_after();
@@ -371,20 +384,30 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
             uint32_t v[32];
             bool have = (cs * 32 + 32 <= p.block_n);
-            if (have) TMEM_LD32(taddr + (uint32_t)(cs * 32), v);
+            if (PF && have) TMEM_LD32(taddr + (uint32_t)(cs * 32), v);
             for (int c = cs; c < nchunks; c += CS) {
                 const int col = c * 32;
                 if (have) {
                     uint32_t w[32];
-                    tmem_ld_wait();
+                    if (PF) {
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) w[i] = v[i];
-                    // prefetch this group's next chunk of the accumulator while the current one is processed
-                    have = ((c + CS) < nchunks && (c + CS) * 32 + 32 <= p.block_n);
-                    if (have) TMEM_LD32(taddr + (uint32_t)(col + 32 * CS), v);
+                        for (int i = 0; i < 32; ++i) w[i] = v[i];
+                        // prefetch this group's next chunk of the accumulator while the current one is processed
+                        have = ((c + CS) < nchunks && (c + CS) * 32 + 32 <= p.block_n);
+                        if (have) TMEM_LD32(taddr + (uint32_t)(col + 32 * CS), v);
+                    } else {
+                        TMEM_LD32(taddr + (uint32_t)col, w);
+                        tmem_ld_wait();
+                        have = ((c + CS) < nchunks && (c + CS) * 32 + 32 <= p.block_n);
+                    }
                     if (tracer) trace(p.dbg, 2, tn, 23);
                     float f[32];
-                    epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col);
+                    epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col, res16 ? rr : nullptr);
+                    if (res16 && have) {                    // `have`: this group has another full chunk in this tile
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + col + 32 * CS + 8 * i);
+                    }
                     if (tracer) trace(p.dbg, 2, tn, 24);
                     if (p.tma_store) {
                         if (lane == 0) bulk_wait_read<1>();      // the store that used this buffer two chunks ago has read it
@@ -549,7 +572,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
-        epilogue_role(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
+        epilogue_role<NT == NT_2WG>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
     }
 
     tc_fence_before();
@@ -694,7 +717,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             acc += 2;   if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
-        epilogue_role(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
+        epilogue_role<false>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
     }
 
     tc_fence_before();
@@ -860,7 +883,7 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             acc += NPAIR; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
-        epilogue_role(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_t, bar_t + 64u);
+        epilogue_role<NT == NT_2WG>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_t, bar_t + 64u);
     }
 
     tc_fence_before();
