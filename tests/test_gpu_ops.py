@@ -207,3 +207,50 @@ def test_nms_api_edges():
     assert all(torch.equal(a, b) for a, b in zip(d1, d2))
     with pytest.raises(ValueError):
         yolo_b200.non_max_suppression(p[0])
+
+
+def test_conv_tcgen05_fuzz_vs_torch_fp32():
+    """Seeded random conv shapes straight through the C ABI (yre_conv, tcgen05 engine): generic, weight-stationary halo,
+    streamed halo and paired-halo schedules, channel windows, residuals, ragged edges -- against a plain torch fp32
+    conv of the same bf16-rounded operands.  Tolerance: output rounding to bf16 (2^-8 relative) + accumulation order."""
+    import ctypes as C
+    import random
+    import torch.nn.functional as F
+    lib = L.lib()
+    rnd = random.Random(5)
+    for it in range(36):
+        k = rnd.choice([1, 3, 3])
+        Cin, Cout = rnd.choice([32, 64, 64, 128, 256]), rnd.choice([32, 64, 128, 160, 256, 320])
+        extra = rnd.choice([0, 0, 32, 64])
+        Ct, coff = Cin + extra, (rnd.choice([0, extra]) if extra else 0)
+        if it % 3 == 0:          # enough exact 8x16 patches for the paired schedule
+            k, Cout = 3, rnd.choice([128, 256])
+            Cin = rnd.choice([64, 128]); Ct, coff = Cin, 0
+            H, W = 16 * rnd.randint(2, 4), 8 * rnd.randint(3, 8)
+            Bn = -(-300 // ((H // 16) * (W // 8)))
+        elif it % 3 == 1:
+            H, W, Bn = 16 * rnd.randint(1, 4), 8 * rnd.randint(1, 8), rnd.choice([1, 2, 3])
+        else:
+            H, W, Bn = rnd.randint(3, 50), rnd.randint(3, 50), rnd.choice([1, 2, 5])
+        act, res = rnd.choice([0, 1]), rnd.choice([0, 1])
+        g = torch.Generator().manual_seed(100 + it)
+        x = torch.randn((Bn, H, W, Ct), generator=g).bfloat16()
+        w = (torch.randn((Cout, k, k, Cin), generator=g) / (k * k * Cin) ** 0.5).bfloat16()
+        bias = torch.randn((Cout,), generator=g)
+        r = torch.randn((Bn, H, W, Cout), generator=g).bfloat16()
+        ref = F.conv2d(x[..., coff:coff + Cin].float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=k // 2)
+        if act:
+            ref = F.silu(ref)
+        if res:
+            ref = ref + r.float().permute(0, 3, 1, 2)
+        xd, wd, bd, rd = x.to(DEV), w.to(DEV), bias.to(DEV), r.to(DEV)
+        y = torch.full((Bn, H, W, Cout), 7.0, dtype=torch.bfloat16, device=DEV)
+        d = L.ConvDesc(L.View(xd.data_ptr(), L.BF16, L.NHWC, Bn, H, W, Ct, coff, Cin),
+                       L.View(y.data_ptr(), L.BF16, L.NHWC, Bn, H, W, Cout, 0, Cout),
+                       L.View(rd.data_ptr(), L.BF16, L.NHWC, Bn, H, W, Cout, 0, Cout) if res else L.View(None, 0, 0, 0, 0, 0, 0, 0, 0),
+                       wd.data_ptr(), bd.data_ptr(), k, 1, act, L.ENGINE_TCGEN05)
+        L.check(lib.yre_conv(C.byref(d), torch.cuda.current_stream().cuda_stream), "yre_conv")
+        got = y.float().cpu().permute(0, 3, 1, 2)
+        err = (got - ref).abs().max().item()
+        assert err <= BF16_CONV_TOL * max(1.0, ref.abs().max().item()), \
+            f"case {it}: B{Bn} {H}x{W} {Cin}(+{extra}@{coff})->{Cout} k{k} act{act} res{res}: max err {err:.4f}"
