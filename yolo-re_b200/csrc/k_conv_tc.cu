@@ -347,6 +347,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);         // SWIZZLE_64B pattern of this row
         const int nchunks = (p.block_n + 31) >> 5;
         const bool tracer = (warp == 4 && lane == 0);
+        const bool tma_store = p.tma_store != 0;
+        const uint32_t stage_out = p.stage_out_bytes;
+        const int block_n = p.block_n, y_coff = p.y_coff;
         uint32_t acc = (uint32_t)tg % NACC, acc_phase = ((uint32_t)tg / NACC) & 1u, obuf = 0;
         int tn = 0;
         TileCur tc;
@@ -382,56 +385,72 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             tc_fence_after();
             if (tracer) trace(p.dbg, 2, tn, 21);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)p.acc_stride;
-            uint32_t v[32];
-            bool have = (cs * 32 + 32 <= p.block_n);
-            if (PF && have) TMEM_LD32(taddr + (uint32_t)(cs * 32), v);
-            for (int c = cs; c < nchunks; c += CS) {
-                const int col = c * 32;
-                if (have) {
-                    uint32_t w[32];
-                    if (PF) {
-                        tmem_ld_wait();
+            // One full 32-column chunk: math -> (next residual) -> staging -> TMA store.  Everything the elected lane passes
+            // to the TMA unit is warp-uniform, so the issue stays on the uniform datapath (no per-lane serialising loop).
+            auto process32 = [&](const uint32_t* w, int col, bool more) {
+                float f[32];
+                epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col, res16 ? rr : nullptr);
+                if (res16 && more) {                      // this group's next full chunk of the tile
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) w[i] = v[i];
-                        // prefetch this group's next chunk of the accumulator while the current one is processed
-                        have = ((c + CS) < nchunks && (c + CS) * 32 + 32 <= p.block_n);
-                        if (have) TMEM_LD32(taddr + (uint32_t)(col + 32 * CS), v);
-                    } else {
-                        TMEM_LD32(taddr + (uint32_t)col, w);
+                    for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + col + 32 * CS + 8 * i);
+                }
+                if (tma_store) {
+                    if (elect_one()) bulk_wait_read<1>();       // the store that used this buffer two chunks ago has read it
+                    __syncwarp();
+                    const uint32_t buf = stg + obuf * stage_out;
+                    store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        tma_store_4d(tmY, buf, y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
+                        bulk_commit();
+                    }
+                    obuf ^= 1u;
+                } else if (valid) {
+                    store_direct<32>(p, f, pix, n0 + col);
+                }
+            };
+            auto tail16 = [&](int col) {                  // 16-column tail (block_n % 32 == 16, direct-store outputs only)
+                uint32_t w16[16];
+                float f[16];
+                TMEM_LD16(taddr + (uint32_t)col, w16);
+                tmem_ld_wait();
+                epilogue_math<16>(p, sbias, w16, f, valid, pix, n0 + col);
+                if (valid) store_direct<16>(p, f, pix, n0 + col);
+            };
+            auto full_at = [&](int c) { return c < nchunks && c * 32 + 32 <= block_n; };
+            if (PF) {
+                // two register buffers, alternately consumed and refilled: the loop is unrolled by two chunks so that no
+                // buffer is ever copied (a rotating single pair cost 64 register moves per chunk)
+                uint32_t va[32], vb[32];
+                int c = cs;
+                bool ha = full_at(c), hb = false;
+                if (ha) TMEM_LD32(taddr + (uint32_t)(c * 32), va);
+                while (c < nchunks) {
+                    if (ha) {
                         tmem_ld_wait();
-                        have = ((c + CS) < nchunks && (c + CS) * 32 + 32 <= p.block_n);
-                    }
-                    if (tracer) trace(p.dbg, 2, tn, 23);
-                    float f[32];
-                    epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col, res16 ? rr : nullptr);
-                    if (res16 && have) {                    // `have`: this group has another full chunk in this tile
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + col + 32 * CS + 8 * i);
-                    }
-                    if (tracer) trace(p.dbg, 2, tn, 24);
-                    if (p.tma_store) {
-                        if (lane == 0) bulk_wait_read<1>();      // the store that used this buffer two chunks ago has read it
-                        __syncwarp();
-                        const uint32_t buf = stg + obuf * p.stage_out_bytes;
-                        store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
-                        fence_async_smem();
-                        __syncwarp();
-                        if (lane == 0) {
-                            tma_store_4d(tmY, buf, p.y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
-                            bulk_commit();
-                        }
-                        obuf ^= 1u;
-                        if (tracer) trace(p.dbg, 2, tn, 26);
-                    } else if (valid) {
-                        store_direct<32>(p, f, pix, n0 + col);
-                    }
-                } else {                         // 16-column tail (block_n % 32 == 16, direct-store outputs only)
-                    uint32_t w16[16];
-                    float f[16];
-                    TMEM_LD16(taddr + (uint32_t)col, w16);
-                    tmem_ld_wait();
-                    epilogue_math<16>(p, sbias, w16, f, valid, pix, n0 + col);
-                    if (valid) store_direct<16>(p, f, pix, n0 + col);
+                        hb = full_at(c + CS);
+                        if (hb) TMEM_LD32(taddr + (uint32_t)((c + CS) * 32), vb);
+                        process32(va, c * 32, hb);
+                    } else { tail16(c * 32); hb = false; }
+                    c += CS;
+                    if (c >= nchunks) break;
+                    if (hb) {
+                        tmem_ld_wait();
+                        ha = full_at(c + CS);
+                        if (ha) TMEM_LD32(taddr + (uint32_t)((c + CS) * 32), va);
+                        process32(vb, c * 32, ha);
+                    } else { tail16(c * 32); ha = false; }
+                    c += CS;
+                }
+            } else {
+                for (int c = cs; c < nchunks; c += CS) {
+                    if (full_at(c)) {
+                        uint32_t w[32];
+                        TMEM_LD32(taddr + (uint32_t)(c * 32), w);
+                        tmem_ld_wait();
+                        process32(w, c * 32, full_at(c + CS));
+                    } else tail16(c * 32);
                 }
             }
             // every tcgen05.ld of this accumulator has completed: hand the TMEM buffer back
@@ -442,7 +461,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             acc += G;
             while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
-        if (p.tma_store && lane == 0) bulk_wait_all();           // stores must land before the CTA retires
+        if (tma_store && elect_one()) bulk_wait_all();            // stores must land before the CTA retires
     }
 
 template <int KSTEPS, int NT>     // KSTEPS = BLOCK_K / 16: 4 (128-byte swizzle) or 2 (64-byte swizzle); NT = threads per CTA
