@@ -172,7 +172,7 @@ __device__ __forceinline__ uint4 bf8_max(uint4 a, uint4 b) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 3) adown_tiled_kernel(DView x, DView lo, DView hi, int half, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(256, sizeof(T) == 2 ? 4 : 3) adown_tiled_kernel(DView x, DView lo, DView hi, int half, int tiles_x, int tiles_y) {
     constexpr int CHN = SmemPix<T>::CHN, G = CHN / 8;
     __shared__ uint4 tile[AD_ROWS][AD_COLS][9];        // 8 x 16 B of data + 16 B pad per pixel
     int t = blockIdx.x;
@@ -189,29 +189,35 @@ __global__ void __launch_bounds__(256, 3) adown_tiled_kernel(DView x, DView lo, 
     // every thread issues ALL of its 16-byte loads into registers first, then stores them to shared memory
     // (a load -> store -> load loop would serialise one HBM round trip per chunk)
     constexpr int NLDS = (AD_ROWS * AD_COLS * 8 + 255) / 256;       // 11
-    uint4 buf[NLDS];
     if (sizeof(T) == 2 && x.layout == YRE_NHWC) {
-        // row-linear addressing: thread (cc = tid/8, v = tid%8) reads column cc of all 10 rows (one pointer, a constant
-        // row stride), threads 0..159 the two extra columns -- no per-load div/mod or 64-bit index arithmetic
+        // row-linear addressing: thread (cc = tid/8, v = tid%8) copies column cc of all 10 rows (one pointer, a constant
+        // row stride), threads 0..159 the two extra columns -- no per-load div/mod or 64-bit index arithmetic.  The copies
+        // are cp.async (zero-fill outside the image): no register staging, so four CTAs fit an SM and one CTA's loads
+        // overlap the arithmetic of the others (ncu: the shared-memory stores waiting on the loads were 28 % of the samples)
         const int v = tid & 7, cc = tid >> 3;
         const long long rs = (long long)x.W * x.C_total;
         const T* col = xp + (((long long)b * x.H + iy0) * x.W + (ix0 + cc)) * x.C_total + x.c_off + c0 + v * 8;
         const bool xin = (ix0 + cc) >= 0 && (ix0 + cc) < x.W;
+        const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(&tile[0][cc][v]);
+        constexpr uint32_t ROWB = AD_COLS * 9 * 16;
 #pragma unroll
         for (int q = 0; q < AD_ROWS; ++q) {
             const int iy = iy0 + q;
-            buf[q] = (xin && iy >= 0 && iy < x.H) ? *reinterpret_cast<const uint4*>(col + q * rs) : make_uint4(0u, 0u, 0u, 0u);
+            const bool in = xin && iy >= 0 && iy < x.H;
+            const T* src = in ? col + q * rs : xp;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(t0 + (uint32_t)q * ROWB), "l"(src), "r"(in ? 16 : 0) : "memory");
         }
-        const int er = tid >> 4, ec = AD_COLS - 2 + ((tid >> 3) & 1);
-        {
+        if (tid < AD_ROWS * 16) {
+            const int er = tid >> 4, ec = AD_COLS - 2 + ((tid >> 3) & 1);
             const int iy = iy0 + er, ix = ix0 + ec;
-            buf[AD_ROWS] = (tid < AD_ROWS * 16 && iy >= 0 && iy < x.H && ix >= 0 && ix < x.W)
-                ? *reinterpret_cast<const uint4*>(xp + (((long long)b * x.H + iy) * x.W + ix) * x.C_total + x.c_off + c0 + v * 8) : make_uint4(0u, 0u, 0u, 0u);
+            const bool in = iy >= 0 && iy < x.H && ix >= 0 && ix < x.W;
+            const T* src = in ? xp + (((long long)b * x.H + iy) * x.W + ix) * x.C_total + x.c_off + c0 + v * 8 : xp;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&tile[er][ec][v])), "l"(src), "r"(in ? 16 : 0) : "memory");
         }
-#pragma unroll
-        for (int q = 0; q < AD_ROWS; ++q) tile[q][cc][v] = buf[q];
-        if (tid < AD_ROWS * 16) tile[er][ec][v] = buf[AD_ROWS];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
+        uint4 buf[NLDS];
 #pragma unroll
         for (int q = 0; q < NLDS; ++q) {
             const int i = tid + 256 * q;
