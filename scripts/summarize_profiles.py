@@ -36,7 +36,7 @@ if f.exists():
     d = collections.OrderedDict()
     for r in rows[hi + 1:]:
         if len(r) > iv:
-            d.setdefault(r[iid], {"k": r[ik].split("(")[0].split("::")[-1]})[r[im]] = float(r[iv].replace(",", ""))
+            d.setdefault(r[iid], {"k": r[ik].split("(")[0].split("::")[-1].replace(", ", ";")})[r[im]] = float(r[iv].replace(",", ""))
     agg = collections.OrderedDict()
     for v in d.values():
         a = agg.setdefault(v["k"], [0, 0.0, 0.0, 0.0])
