@@ -182,3 +182,45 @@ def test_block_plans(dry, prec):
         tol = 1e-4 if prec == "fp32" else 6e-2
         assert out.shape == ref.shape
         assert (out - ref).abs().max() <= tol * max(1.0, ref.abs().max().item()), (type(m).__name__, (out - ref).abs().max())
+
+
+# ---- checkpoint ingestion --------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["gelan-c", "yolov9-c"])
+def test_upstream_checkpoint_keys_match_reference_converter(cfg):
+    """Key-for-key equality with the reference's scripts/convert_weights.py on the same upstream key list
+    (fixture produced by the reference function, tests/golden/make_golden_ckpt.py)."""
+    import json
+    from yolo_b200 import convert_upstream_state_dict
+    pairs = json.loads((ROOT / "tests/golden/ckpt_keys.json").read_text())[cfg]
+    m = YOLO.from_yaml(ROOT / f"configs/models/{cfg}.yaml")
+    upstream = {u: i for i, (u, _) in enumerate(pairs)}
+    upstream["model.999.foo"] = -1           # index beyond the graph: skipped
+    upstream["optimizer.state"] = -2         # not a model key: skipped
+    weightless = next(i for i, mod in enumerate(m.layers.values()) if not list(mod.state_dict()))
+    upstream[f"model.{weightless}.whatever"] = -3       # weight-less node (Upsample / Concat / Silence ...): skipped
+    got = convert_upstream_state_dict(upstream, m)
+    assert list(got.keys()) == [r for _, r in pairs]
+    assert list(got.values()) == list(range(len(pairs)))
+    assert set(got.keys()) == set(m.state_dict().keys())
+
+
+def test_load_checkpoint_layouts(gelan_c, tmp_path):
+    """Upstream layout (dict or {'model': dict}), reference training checkpoint and plain state_dict all load strictly."""
+    import json
+    from yolo_b200 import load_checkpoint
+    nodes, nc, sd = gelan_c
+    pairs = json.loads((ROOT / "tests/golden/ckpt_keys.json").read_text())["gelan-c"]
+    upstream = {u: sd[r] for u, r in pairs}
+    for ck in (upstream, {"model": upstream, "epoch": 3}, {"model_state_dict": sd}, sd):
+        m = load_checkpoint(YOLO.from_yaml(ROOT / "configs/models/gelan-c.yaml"), ck)
+        back = m.state_dict()
+        assert all(torch.equal(back[k], sd[k]) for k in sd)
+    path = tmp_path / "up.pt"
+    torch.save({"model": upstream}, path)
+    m = load_checkpoint(YOLO.from_yaml(ROOT / "configs/models/gelan-c.yaml"), path)
+    assert torch.equal(m.state_dict()["layers.detect.dfl.conv.weight"], sd["layers.detect.dfl.conv.weight"])
+    with pytest.raises(ValueError):
+        load_checkpoint(m, {"foo": torch.zeros(1)})
+    bad = dict(upstream); bad.pop(pairs[0][0])
+    with pytest.raises(RuntimeError):
+        load_checkpoint(YOLO.from_yaml(ROOT / "configs/models/gelan-c.yaml"), bad)           # strict: a missing key is an error

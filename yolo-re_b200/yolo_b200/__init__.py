@@ -8,7 +8,8 @@ from .engine import precision
 from .model import BLOCKS, YOLO, ModelConfig, build_layers, parse_yaml
 from .nms import nms_raw, non_max_suppression
 from .preprocess import letterbox, preprocess, scale_boxes
+from .checkpoint import convert_upstream_state_dict, load_checkpoint
 
 __version__ = "0.1.0"
 __all__ = ["YOLO", "non_max_suppression", "nms_raw", "precision", "YreError", "lib", "ModelConfig", "parse_yaml",
-           "build_layers", "BLOCKS", "letterbox", "preprocess", "scale_boxes"]
+           "build_layers", "BLOCKS", "letterbox", "preprocess", "scale_boxes", "convert_upstream_state_dict", "load_checkpoint"]
