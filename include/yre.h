@@ -196,6 +196,29 @@ int yre_letterbox_u8_batch(const yre_letterbox_desc* d, int32_t n, yre_stream_t 
 int yre_scale_boxes(float* boxes, int32_t n, int32_t row_stride, float pad_w, float pad_h, float gain,
                     float orig_w, float orig_h, yre_stream_t s);
 
+/* ---- K11: detection -> ground-truth matching for mAP ------------------------------
+ * Replaces the per-prediction loop of compute_map        src/yolo/eval/metrics.py:137-176
+ *          box_iou                                        src/yolo/eval/metrics.py:10-31
+ * det: fp32 rows [x1,y1,x2,y2,conf,cls], `det_stride` floats apart, the images' rows concatenated; det_off: int32
+ * [B+1] row ranges.  Rows of one image must be in matching order = descending score, ties in original order (what
+ * yre_nms_batched emits).  gt_boxes fp32 [M][4] xyxy (16-byte aligned), gt_cls int32 [M], gt_off int32 [B+1].
+ * thr: n_thr <= 16 IoU thresholds (doubles, compared after a cast to fp32 exactly like torch's `best_iou >= thr`).
+ * tp: uint8 [N][n_thr]: 1 = true positive at that threshold.  max_gt_per_image: host-known bound (<= 4096). */
+typedef struct yre_match_desc {
+    const float*   det;
+    int32_t        det_stride;
+    const int32_t* det_off;
+    const float*   gt_boxes;
+    const int32_t* gt_cls;
+    const int32_t* gt_off;
+    int32_t        B;
+    int32_t        n_thr;
+    double         thr[16];
+    int32_t        max_gt_per_image;
+    uint8_t*       tp;
+} yre_match_desc;
+int yre_match_detections(const yre_match_desc* d, yre_stream_t s);
+
 /* ---- flat launch plan -------------------------------------------------------------------------
  * Replaces the named-DAG interpreter loop of YOLO.forward  src/yolo/model/model.py:87-107
  * The host walks the module tree once, records every op (descriptors are copied, TMA tensor

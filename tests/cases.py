@@ -88,3 +88,44 @@ def preproc_boxes(S: int, seed: int, n: int = 64):
     rng = np.random.default_rng(1000 + seed)
     c = rng.uniform(-20, S + 20, (n, 2)); wh = rng.uniform(2, S / 2, (n, 2))
     return np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+
+
+# ---- detection-metric cases: name -> (images, classes, max detections/img, max gts/img, seed) --------
+METRIC_CASES = {
+    "small": (4, 3, 12, 6, 1),
+    "coco_like": (16, 80, 300, 40, 2),
+    "ties": (6, 2, 40, 10, 3),            # quantised scores (ties across images) and boxes snapped to a grid (IoU ties)
+    "empty_mix": (8, 5, 20, 8, 4),        # some images without detections, some without ground truth
+}
+
+
+def metric_case(name: str):
+    """(pred_boxes, pred_scores, pred_classes, gt_boxes, gt_classes, num_classes) as lists of numpy arrays; detections
+    per image in descending-score order (what NMS returns)."""
+    import numpy as np
+    n_img, nc, max_det, max_gt, seed = METRIC_CASES[name]
+    rng = np.random.default_rng(seed)
+    pb, ps, pc, gb, gc = [], [], [], [], []
+    for i in range(n_img):
+        m = int(rng.integers(0, max_gt + 1)) if not (name == "empty_mix" and i % 3 == 0) else 0
+        c = rng.uniform(40, 600, (m, 2)); wh = rng.uniform(10, 200, (m, 2))
+        g = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        gcl = rng.integers(0, nc, m).astype(np.int64)
+        n = int(rng.integers(0, max_det + 1)) if not (name == "empty_mix" and i % 4 == 1) else 0
+        # detections: jittered copies of ground truths (some with the wrong class) plus random boxes
+        src = rng.integers(0, max(m, 1), n)
+        jit = rng.normal(0, 12, (n, 4)).astype(np.float32)
+        d = (g[src] + jit) if m else np.zeros((n, 4), np.float32)
+        rnd = rng.random(n) < 0.35
+        c2 = rng.uniform(40, 600, (n, 2)); wh2 = rng.uniform(10, 200, (n, 2))
+        d = np.where(rnd[:, None] | (m == 0), np.concatenate([c2 - wh2 / 2, c2 + wh2 / 2], 1), d).astype(np.float32)
+        d[:, 2:] = np.maximum(d[:, 2:], d[:, :2] + 1)
+        dcl = np.where(rng.random(n) < 0.8, gcl[src] if m else rng.integers(0, nc, n), rng.integers(0, nc, n)).astype(np.int64)
+        sc = rng.random(n).astype(np.float32)
+        if name == "ties":
+            sc = (np.round(sc * 8) / 8).astype(np.float32)
+            d = (np.round(d / 16) * 16).astype(np.float32); d[:, 2:] = np.maximum(d[:, 2:], d[:, :2] + 16)
+            g = (np.round(g / 16) * 16).astype(np.float32); g[:, 2:] = np.maximum(g[:, 2:], g[:, :2] + 16)
+        o = np.argsort(-sc, kind="stable")
+        pb.append(d[o]); ps.append(sc[o]); pc.append(dcl[o]); gb.append(g); gc.append(gcl)
+    return pb, ps, pc, gb, gc, nc

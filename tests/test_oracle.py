@@ -176,3 +176,33 @@ def test_letterbox_geometry_c_helper_matches_python_arithmetic():
             continue
         assert rc == 0, (h, w, S, L.lib().yre_last_error())
         assert (d.new_w, d.new_h, d.top, d.left, rr.value, (pw.value, ph.value)) == (nw, nh, top, left, r, pad), (h, w, S)
+
+
+# ---- detection-metric oracle -------------------------------------------------------------
+from oracle import metrics_ref as MR  # noqa: E402
+from tests.cases import METRIC_CASES, metric_case  # noqa: E402
+
+MET_GOLD = np.load(Path(__file__).resolve().parent / "golden" / "metrics_cases.npz")
+
+
+@pytest.mark.parametrize("name", list(METRIC_CASES))
+def test_metrics_oracle_matches_reference_fixture(name):
+    """oracle compute_map == the REFERENCE's compute_map, bit for bit in float64 (make_golden_metrics.py)."""
+    a = metric_case(name)
+    r, r7 = MR.compute_map(*a), MR.compute_map(*a, iou_thresholds=[0.7])
+    assert np.array_equal(np.array([r["map50"], r["map75"], r["map"], r7["map"]]), MET_GOLD[name])
+
+
+def test_metrics_host_aggregation_matches_oracle():
+    """The vectorised AP / aggregation used by the product (yolo_b200.metrics._aggregate, host numpy) fed with the ORACLE's
+    match flags reproduces the oracle's result bit for bit -- checks the host half of the fast path without a GPU."""
+    import yolo_b200  # noqa: F401
+    from yolo_b200.metrics import _aggregate
+    for name in METRIC_CASES:
+        pb, ps, pc, gb, gc, nc = metric_case(name)
+        thr = [0.5 + 0.05 * i for i in range(10)]
+        tp = np.concatenate([MR.match_image(pb[i], pc[i], gb[i], gc[i], thr) for i in range(len(pb))]) if sum(map(len, pb)) else np.zeros((0, 10), np.uint8)
+        off = np.concatenate([[0], np.cumsum([len(x) for x in pb])]).astype(np.int32)
+        got = _aggregate(np.concatenate(ps), np.concatenate(pc), tp, off, gc, nc, thr)
+        ref = MR.compute_map(pb, ps, pc, gb, gc, nc)
+        assert got == ref, name

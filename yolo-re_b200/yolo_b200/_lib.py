@@ -53,6 +53,12 @@ class LetterboxDesc(C.Structure):
 
 LB_F32_CHW, LB_U8_HWC = 0, 1
 
+
+class MatchDesc(C.Structure):
+    _fields_ = [("det", C.c_void_p), ("det_stride", C.c_int32), ("det_off", C.c_void_p), ("gt_boxes", C.c_void_p),
+                ("gt_cls", C.c_void_p), ("gt_off", C.c_void_p), ("B", C.c_int32), ("n_thr", C.c_int32), ("thr", C.c_double * 16),
+                ("max_gt_per_image", C.c_int32), ("tp", C.c_void_p)]
+
 # name -> (restype, argtypes); every symbol include/yre.h declares
 SYMBOLS = {
     "yre_version": (C.c_int, []),
@@ -73,6 +79,7 @@ SYMBOLS = {
     "yre_letterbox_u8": (C.c_int, [C.POINTER(LetterboxDesc), C.c_void_p]),
     "yre_letterbox_u8_batch": (C.c_int, [C.POINTER(LetterboxDesc), C.c_int32, C.c_void_p]),
     "yre_scale_boxes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "yre_match_detections": (C.c_int, [C.POINTER(MatchDesc), C.c_void_p]),
     "yre_plan_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "yre_plan_destroy": (None, [C.c_void_p]),
     "yre_plan_add_conv": (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
