@@ -18,6 +18,12 @@ NCCL only gathers the timing.  Prints ONE JSON line (rank 0).
 
 `--impl reference` times the reference algorithm's CPU port (oracle/, the reference itself is pure
 Python/PyTorch and is not present on the GPU box) on the same config/metric.
+
+Use of oracle/ here: (1) the cpu_baseline leg and the reference arm execute it (that is what they measure);
+(2) both arms take their SYNTHETIC DATA from it -- `calibrated_state_dict` (the calibrated random-init weight recipe of
+SURVEY.md 8d, which needs one CPU train-mode forward to set the BatchNorm statistics) and the graph description it is
+built from -- so that the two arms run the same weights.  No number of the timed GPU path is computed by oracle/: the
+product (yolo_b200 + libyre.so) never imports it and fails loudly without the CUDA library.
 """
 from __future__ import annotations
 
