@@ -224,3 +224,30 @@ def test_load_checkpoint_layouts(gelan_c, tmp_path):
     bad = dict(upstream); bad.pop(pairs[0][0])
     with pytest.raises(RuntimeError):
         load_checkpoint(YOLO.from_yaml(ROOT / "configs/models/gelan-c.yaml"), bad)           # strict: a missing key is an error
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """ABI drift guard: sizeof / offsetof of every descriptor in include/yre.h (compiled with gcc) equal the ctypes mirrors."""
+    import ctypes as C
+    import subprocess
+    from yolo_b200 import _lib as L
+    structs = {"yre_view": (L.View, ["ptr", "dtype", "c_off", "C"]),
+               "yre_conv_desc": (L.ConvDesc, None), "yre_stem_desc": (L.StemDesc, None), "yre_decode_desc": (L.DecodeDesc, None),
+               "yre_nms_desc": (L.NmsDesc, ["pred", "conf_thres", "iou_thres", "max_det", "classes", "out", "workspace_bytes"]),
+               "yre_letterbox_desc": (L.LetterboxDesc, ["src", "row_pitch", "new_shape", "top", "color", "out_mode", "dst"]),
+               "yre_match_desc": (L.MatchDesc, ["det", "det_stride", "gt_off", "B", "thr", "max_gt_per_image", "tp"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "yre.h"}"', "int main(void) {"]
+    for name, (ct, fields) in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for f in fields or []:
+            lines.append(f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    subprocess.run(["gcc", "-o", str(tmp_path / "abi"), str(src)], check=True)
+    out = subprocess.run([str(tmp_path / "abi")], check=True, capture_output=True, text=True).stdout
+    got = dict(l.split() for l in out.strip().splitlines())
+    for name, (ct, fields) in structs.items():
+        assert int(got[name]) == C.sizeof(ct), name
+        for f in fields or []:
+            assert int(got[f"{name}.{f}"]) == getattr(ct, f).offset, f"{name}.{f}"
