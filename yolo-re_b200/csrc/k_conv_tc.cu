@@ -199,14 +199,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                  : "r"(addr) : "memory")
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// SiLU with ONE MUFU op per element: x*sigmoid(x) = 0.5x * (1 + tanh(0.5x)).
-__device__ __forceinline__ float silu_fast(float x) {
-    const float h = 0.5f * x;
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
-}
-
 // Tile cursor: (nt, xt, yt, bt) of tile index t, advanced by a constant stride without div/mod.
 struct TileCur {
     int nt, xt, yt, bt;

@@ -136,8 +136,8 @@ template <> struct SmemPix<float> {
     }
 };
 
-// packed bf16x2 helpers for the bf16 product path of K3: the 2x2 average is formed with three HADD2
-// (each rounds to bf16: two roundings more than an fp32 sum, <= 3 * 2^-9 relative) and one exact x0.25;
+// packed bf16x2 helpers for the bf16 product path of K3: the 2x2 average is formed with three HADD2 (horizontal pair
+// sums, then their sum; each rounds to bf16: two roundings more than an fp32 sum, <= 3 * 2^-9 relative) and one exact x0.25;
 // the 3x3 max is exact.  This quarters the instruction count of this issue-bound kernel; the fp32
 // validation path keeps torch's exact summation order.
 __device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
@@ -152,14 +152,6 @@ __device__ __forceinline__ uint32_t bf2_quarter(uint32_t a) {
 __device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
     __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
     return *reinterpret_cast<uint32_t*>(&r);
-}
-__device__ __forceinline__ uint4 bf8_avg4(uint4 a, uint4 b, uint4 c, uint4 d) {
-    uint4 r;
-    r.x = bf2_quarter(bf2_add(bf2_add(bf2_add(a.x, b.x), c.x), d.x));
-    r.y = bf2_quarter(bf2_add(bf2_add(bf2_add(a.y, b.y), c.y), d.y));
-    r.z = bf2_quarter(bf2_add(bf2_add(bf2_add(a.z, b.z), c.z), d.z));
-    r.w = bf2_quarter(bf2_add(bf2_add(bf2_add(a.w, b.w), c.w), d.w));
-    return r;
 }
 __device__ __forceinline__ uint4 bf8_add(uint4 a, uint4 b) {
     return make_uint4(bf2_add(a.x, b.x), bf2_add(a.y, b.y), bf2_add(a.z, b.z), bf2_add(a.w, b.w));
