@@ -52,3 +52,44 @@ def test_unsorted_predictions_and_accumulator():
     assert DetectionAccumulator(3).compute() == {"map50": 0.0, "map75": 0.0, "map": 0.0}
     with pytest.raises(yolo_b200.YreError):
         match_detections([torch.zeros((2, 6))], [torch.zeros((1, 4))], [torch.zeros(1)], THR)      # CPU detections: no fallback
+
+
+def test_evaluator_flow_matches_reference_arithmetic():
+    """Evaluator.evaluate() (reference src/yolo/eval/evaluator.py:96-199 flow on the device) == the oracle's compute_map fed
+    with the same model's detections and the reference's CPU ground-truth conversion."""
+    from oracle import gelan_ref as G
+    from yolo_b200 import YOLO, Evaluator, non_max_suppression
+    root = Path(__file__).resolve().parents[1]
+    nodes, nc = G.load_graph(root / "configs/models/gelan-c.yaml")
+    m = YOLO.from_yaml(root / "configs/models/gelan-c.yaml")
+    m.load_state_dict(G.calibrated_state_dict(nodes, nc))
+    rng = np.random.default_rng(5)
+    S, batches = 256, []
+    for bi in range(2):
+        imgs = G.fractal(3, S, torch.Generator().manual_seed(30 + bi))
+        rows = []
+        for i in range(3):
+            k = int(rng.integers(0, 6))
+            cxy, wh = rng.uniform(0.2, 0.8, (k, 2)), rng.uniform(0.05, 0.4, (k, 2))
+            rows += [[i, int(rng.integers(0, nc)), *cxy[j], *wh[j]] for j in range(k)]
+        batches.append((imgs, torch.tensor(rows, dtype=torch.float32).reshape(-1, 6), None, [(S, S)] * 3))
+    got = Evaluator(m, batches, num_classes=nc, conf_thres=0.25, iou_thres=0.45).evaluate()
+    # the same flow with the reference's host-side arithmetic and the oracle's metric code
+    pb, ps, pc, gb, gc = [], [], [], [], []
+    m = m.cuda().eval()
+    for imgs, targets, _, _ in batches:
+        y, _ = m(imgs.cuda())
+        dets = non_max_suppression(y.permute(0, 2, 1).contiguous(), 0.25, 0.45)
+        for i in range(imgs.shape[0]):
+            d = dets[i].cpu().numpy()
+            pb.append(d[:, :4]); ps.append(d[:, 4]); pc.append(d[:, 5].astype(np.int64))
+            t = targets[targets[:, 0] == i]
+            xywh = t[:, 2:6].clone()
+            xywh[:, [0, 2]] *= S; xywh[:, [1, 3]] *= S
+            xyxy = torch.zeros_like(xywh)
+            xyxy[:, 0] = xywh[:, 0] - xywh[:, 2] / 2; xyxy[:, 1] = xywh[:, 1] - xywh[:, 3] / 2
+            xyxy[:, 2] = xywh[:, 0] + xywh[:, 2] / 2; xyxy[:, 3] = xywh[:, 1] + xywh[:, 3] / 2
+            gb.append(xyxy.numpy()); gc.append(t[:, 1].long().numpy())
+    assert got == MR.compute_map(pb, ps, pc, gb, gc, nc)
+    with pytest.raises(NotImplementedError):
+        Evaluator(m, batches, debug_dir="/tmp/x")

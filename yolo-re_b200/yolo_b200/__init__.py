@@ -9,8 +9,8 @@ from .model import BLOCKS, YOLO, ModelConfig, build_layers, parse_yaml
 from .nms import nms_raw, non_max_suppression
 from .preprocess import letterbox, preprocess, scale_boxes
 from .checkpoint import convert_upstream_state_dict, load_checkpoint
-from .metrics import DetectionAccumulator, compute_map, match_detections
+from .metrics import DetectionAccumulator, Evaluator, compute_map, match_detections
 
 __version__ = "0.1.0"
 __all__ = ["YOLO", "non_max_suppression", "nms_raw", "precision", "YreError", "lib", "ModelConfig", "parse_yaml",
-           "build_layers", "BLOCKS", "letterbox", "preprocess", "scale_boxes", "convert_upstream_state_dict", "load_checkpoint", "compute_map", "match_detections", "DetectionAccumulator"]
+           "build_layers", "BLOCKS", "letterbox", "preprocess", "scale_boxes", "convert_upstream_state_dict", "load_checkpoint", "compute_map", "match_detections", "DetectionAccumulator", "Evaluator"]

@@ -153,3 +153,52 @@ class DetectionAccumulator:
         flat = torch.cat(self.dets)
         return _aggregate(flat[:, 4].cpu().numpy(), flat[:, 5].long().cpu().numpy(), tp.cpu().numpy(), det_off.numpy(),
                           [g.cpu().numpy() for g in self.gt_classes], self.num_classes, self.iou_thresholds)
+
+
+class Evaluator:
+    """Device-side mirror of the reference's Evaluator (src/yolo/eval/evaluator.py:23-213): same constructor arguments and
+    `evaluate()` result.  Every batch runs model -> NMS on the GPU and the detections never leave it until the final
+    aggregation (the reference copies every image's detections to the CPU and loops over predictions in Python).
+    The dataloader yields `(images [B,3,S,S] float in [0,1], targets [n,6] = (image index, class, cx, cy, w, h normalised),
+    _, orig_shapes)` exactly like the reference's (evaluator.py:96, 133-150).  Debug visualisation is out of scope."""
+
+    def __init__(self, model, dataloader, num_classes: int = 80, conf_thres: float = 0.001, iou_thres: float = 0.6,
+                 device="cuda", debug_dir=None):
+        if debug_dir is not None:
+            raise NotImplementedError("debug visualisation is outside the B200 hot path (SURVEY.md section 2)")
+        self.model, self.dataloader, self.num_classes = model, dataloader, num_classes
+        self.conf_thres, self.iou_thres = conf_thres, iou_thres
+        self.device = torch.device("cuda" if device == "auto" else device)
+        if self.device.type != "cuda":
+            raise L.YreError("Evaluator: the B200 path needs a CUDA device (no CPU fallback)")
+        self.model.to(self.device)
+
+    @torch.no_grad()
+    def evaluate(self, epoch: int = 0) -> dict[str, float]:
+        from .nms import non_max_suppression
+        self.model.eval()
+        acc = DetectionAccumulator(self.num_classes)
+        for images, targets, _, _orig_shapes in self.dataloader:
+            images = images.to(self.device, non_blocking=True)
+            bsz, img_size = images.shape[0], images.shape[2]
+            outputs = self.model(images)
+            if not isinstance(outputs, tuple):
+                raise NotImplementedError("Raw feature map decoding not implemented")     # evaluator.py:113-115
+            preds = outputs[0]
+            if isinstance(preds, list):
+                preds = preds[1]                                                           # main branch (evaluator.py:107-109)
+            dets = non_max_suppression(preds.permute(0, 2, 1).contiguous(), conf_thres=self.conf_thres, iou_thres=self.iou_thres)
+            targets = targets.to(self.device)
+            gtb, gtc = [], []
+            for i in range(bsz):
+                t = targets[targets[:, 0] == i]
+                xywh = t[:, 2:6].float() * img_size                                       # evaluator.py:139-141 (same fp32 ops)
+                xyxy = torch.zeros_like(xywh)
+                xyxy[:, 0] = xywh[:, 0] - xywh[:, 2] / 2
+                xyxy[:, 1] = xywh[:, 1] - xywh[:, 3] / 2
+                xyxy[:, 2] = xywh[:, 0] + xywh[:, 2] / 2
+                xyxy[:, 3] = xywh[:, 1] + xywh[:, 3] / 2
+                gtb.append(xyxy)
+                gtc.append(t[:, 1].long())
+            acc.update(dets, gtb, gtc)
+        return acc.compute()
