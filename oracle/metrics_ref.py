@@ -27,17 +27,19 @@ def box_iou(b1: np.ndarray, b2: np.ndarray) -> np.ndarray:
 
 
 def compute_ap(recall: np.ndarray, precision: np.ndarray) -> float:
-    mrec = np.concatenate(([0.0], recall, [1.0]))
-    mpre = np.concatenate(([1.0], precision, [0.0]))
-    for i in range(len(mpre) - 2, -1, -1):
-        mpre[i] = max(mpre[i], mpre[i + 1])
-    ts = np.linspace(0, 1, 101)
-    out = np.zeros_like(ts)
-    for i, t in enumerate(ts):
-        idx = np.where(mrec >= t)[0]
-        if len(idx) > 0:
-            out[i] = mpre[idx[0]]
-    return float(out.mean())
+    """COCO-style AP: precision envelope (running maximum from the right, with the (0,1) and (1,0) sentinels) sampled at
+    the 101 recall levels 0, 0.01, ..., 1 -- at each level the envelope value of the first point whose recall reaches it."""
+    import bisect
+    rec = [0.0] + [float(v) for v in recall] + [1.0]
+    env = [1.0] + [float(v) for v in precision] + [0.0]
+    for k in reversed(range(len(env) - 1)):
+        if env[k + 1] > env[k]:
+            env[k] = env[k + 1]
+    samples = []
+    for level in np.linspace(0, 1, 101):
+        k = bisect.bisect_left(rec, level)             # recall is non-decreasing
+        samples.append(env[k] if k < len(rec) else 0.0)
+    return float(np.asarray(samples, np.float64).mean())
 
 
 def match_image(pred_boxes, pred_classes, gt_boxes, gt_classes, thresholds):
