@@ -45,3 +45,13 @@ def test_aggregate_throughput_two_ranks_gloo():
     for r in (0, 1):
         ips, total, tmax = res[r]
         assert total == 10 and tmax == 1.0 and ips == 10.0     # SUM of images / MAX of elapsed
+
+
+def test_numa_binding_helper_never_raises_without_a_gpu():
+    """bind_to_gpu_numa_node is best effort: on a box without NVML / CUDA it returns None and leaves the affinity alone."""
+    import os
+    from yolo_b200.shard import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), list)
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
