@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define YRE_VERSION 100
+#define YRE_VERSION 200
 
 typedef void* yre_stream_t; /* cudaStream_t */
 
@@ -81,10 +81,13 @@ typedef struct yre_conv_desc {
 } yre_conv_desc;
 int yre_conv(const yre_conv_desc* d, yre_stream_t s);
 
-/* ---- K2: first conv straight from the fp32 NCHW image -----------------------------------------
+/* ---- K2: first conv straight from the image ------------------------------------------------------
  * Replaces layers.stem1 (Conv 3x3 s2 on the input image; configs/models/gelan-c.yaml stem1,
  * src/yolo/blocks/conv.py:88-89).  x_nchw: fp32 [B][Cin<=4][H][W]; w: fp32 [Cout][3][3][Cin];
- * y may be YRE_NHWC or YRE_PHASE4, bf16 or fp32. */
+ * y may be YRE_NHWC or YRE_PHASE4, bf16 or fp32.
+ * x_u8_hwc (optional; when non-NULL it is the input and x_nchw is ignored): uint8 [B][H][W][3] frames in BGR
+ * order (cv2.imread layout), Cin must be 3.  Fuses what the reference does on the host before model()
+ * (scripts/detect.py:223-227): BGR->RGB, HWC->CHW, .float() / 255 (fp32 division, round to nearest). */
 typedef struct yre_stem_desc {
     const float* x_nchw;
     int32_t      B, Cin, H, W;
@@ -92,6 +95,7 @@ typedef struct yre_stem_desc {
     const float* w;
     const float* bias;
     int32_t      stride, act;
+    const uint8_t* x_u8_hwc;
 } yre_stem_desc;
 int yre_stem_conv(const yre_stem_desc* d, yre_stream_t s);
 
@@ -159,9 +163,18 @@ typedef struct yre_nms_desc {
     int64_t*       keep_anchor;
     void*          workspace;
     size_t         workspace_bytes;
+    /* optional (may be NULL): fp32 [B][5] = (pad_w, pad_h, gain, orig_w, orig_h) per image.  When given, the kept
+     * boxes are written mapped back to the original image -- scale_boxes (scripts/detect.py:74-109) fused into the
+     * output pass with the arithmetic of yre_scale_boxes: clamp((v - pad) / gain, 0, orig), fp32, true division.
+     * Suppression itself always runs on the un-scaled boxes, as in the reference. */
+    const float*   scale;
 } yre_nms_desc;
 size_t yre_nms_workspace_bytes(int32_t B, int32_t A);
 int    yre_nms_batched(const yre_nms_desc* d, yre_stream_t s);
+/* Only the candidate pass of yre_nms_batched (counters reset + filter / argmax / compaction into the workspace):
+ * the HBM-bound stage on its own, for stage timing (bench.py roofline.stages) and profiling.  d->out / counts /
+ * keep_anchor are not touched. */
+int    yre_nms_filter_only(const yre_nms_desc* d, yre_stream_t s);
 
 /* ---- K8/K9: the steps either side of the path -----------------------------------
  * K8 replaces letterbox                                  scripts/detect.py:40-71

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libyre.so does not export {name}"
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
-    assert lib.yre_version() == 100
+    assert lib.yre_version() == 200
     assert lib.yre_nms_workspace_bytes(2, 8400) > 2 * 8400 * 8
 
 
@@ -232,8 +232,8 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     import subprocess
     from yolo_b200 import _lib as L
     structs = {"yre_view": (L.View, ["ptr", "dtype", "c_off", "C"]),
-               "yre_conv_desc": (L.ConvDesc, None), "yre_stem_desc": (L.StemDesc, None), "yre_decode_desc": (L.DecodeDesc, None),
-               "yre_nms_desc": (L.NmsDesc, ["pred", "conf_thres", "iou_thres", "max_det", "classes", "out", "workspace_bytes"]),
+               "yre_conv_desc": (L.ConvDesc, None), "yre_stem_desc": (L.StemDesc, ["x_nchw", "y", "w", "stride", "x_u8_hwc"]), "yre_decode_desc": (L.DecodeDesc, None),
+               "yre_nms_desc": (L.NmsDesc, ["pred", "conf_thres", "iou_thres", "max_det", "classes", "out", "workspace_bytes", "scale"]),
                "yre_letterbox_desc": (L.LetterboxDesc, ["src", "row_pitch", "new_shape", "top", "color", "out_mode", "dst"]),
                "yre_match_desc": (L.MatchDesc, ["det", "det_stride", "gt_off", "B", "thr", "max_gt_per_image", "tp"])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "yre.h"}"', "int main(void) {"]

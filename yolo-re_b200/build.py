@@ -20,6 +20,10 @@ OBJ = HERE / "build"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+# YRE_TUNING=1 at BUILD time compiles the YRE_TC_* / YRE_STEM_* environment knobs and the trace reader in
+# (kernel tuning sessions only); the product build reads no environment variables.
+if os.environ.get("YRE_TUNING", "0") not in ("", "0"):
+    FLAGS.append("-DYRE_TUNING")
 
 
 def _digest() -> str:

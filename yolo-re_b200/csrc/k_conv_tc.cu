@@ -74,6 +74,10 @@ struct TcParams {
     // npair == 2: two patches share every weight box (two accumulators fed per box, half the weight traffic per pixel).
     int npair, upn, num_units, mtiles;
     uint32_t halo_tx;               // bytes one halo box delivers (10 x 18 pixels x BLOCK_K channels)
+    // CTA-pair variant of the generic kernel (cta_group::2): a cluster of two CTAs takes UNIT u -> N tile u % tiles_n,
+    // M tiles 2 * (u / tiles_n) + {0, 1} (cluster rank); each CTA stages its own 128-pixel A tile and block_n / 2 rows of
+    // the weight tile, the leader issues 256 x block_n MMAs.  num_units = tiles_n * ceil(mtiles / 2).
+    int cta2;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -131,6 +135,34 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+// ---- CTA pair (cta_group::2) variants: the two CTAs of a cluster feed ONE 256-row MMA.  The data lands in the issuing
+// CTA's own shared memory, the transaction bytes are counted on the LEADER's (cluster rank 0) mbarrier: clearing bit 24
+// of a shared-window address selects the even CTA of the pair.
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_cg2(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the LEADER CTA's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -178,6 +210,20 @@ __device__ __forceinline__ void umma_bf16_ab(uint32_t tmem_d, uint32_t a_lo, uin
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// CTA pair: one 256 x N x 16 MMA across both SMs (each supplies its 128 rows of A and its N/2 rows of B, read through the
+// same shared-memory offsets in both CTAs); issued by the leader CTA only.
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of the pair's MMAs is signalled on the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
 #define TMEM_LD32(addr, v)                                                                                        \
@@ -320,7 +366,7 @@ __device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base
 // full / empty mbarrier (8 bytes apart per buffer).
 // PF: prefetch the next chunk's tcgen05.ld into a second 32-register buffer (the 168-register / 384-thread kernels); the
 // 512-thread kernels have 128 registers per thread and at most two chunks per tile, so they load each chunk in place.
-template <bool PF>
+template <bool PF, bool CTA2 = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* tmY, const float* sbias, int warp, int lane,
                                               uint32_t tmem_base, uint32_t out_base, uint32_t tfull0, uint32_t tempty0) {
         // ================= epilogue (warp-local, no CTA barrier) =================
@@ -347,9 +393,16 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
         TileCur tc;
         tc.init(p, blockIdx.x + tg * (int)gridDim.x, (int)(G * gridDim.x));
         const bool units = p.halo == 2;          // unit schedule of conv3_halo_stream_kernel (see TcParams)
+        const int pair_rank = CTA2 ? (int)cluster_ctarank() : 0;
         for (int t = blockIdx.x + tg * (int)gridDim.x, j = tg; ; t += (int)(G * gridDim.x), j += (int)G, tc.step(p)) {
             int x0, y0, b0, n0;
-            if (units) {
+            if (CTA2) {                           // CTA-pair schedule: cluster c takes units c, c + #clusters, ...
+                const int u = (int)(blockIdx.x >> 1) + j * (int)(gridDim.x >> 1);
+                if (u >= p.num_units) break;
+                const int m = 2 * (u / p.tiles_n) + pair_rank;       // m >= mtiles (odd tile out): loads zero-fill, stores clip
+                const int r = m / p.tiles_x;
+                x0 = (m % p.tiles_x) * p.tw; y0 = (r % p.tiles_y) * p.th; b0 = (r / p.tiles_y) * p.tb; n0 = (u % p.tiles_n) * p.block_n;
+            } else if (units) {
                 const int P = (int)blockIdx.x + (j / p.npair) * (int)gridDim.x;
                 if (P >= p.num_units) break;
                 const int m = p.npair * (P % p.upn) + (j % p.npair);
@@ -448,7 +501,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             // every tcgen05.ld of this accumulator has completed: hand the TMEM buffer back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty);
+            if (lane == 0) { if (CTA2) mbar_arrive_leader(tempty); else mbar_arrive(tempty); }    // the issuer lives in the leader CTA
             if (tracer) trace(p.dbg, 2, tn, 22);
             acc += G;
             while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
@@ -456,11 +509,15 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
         if (tma_store && elect_one()) bulk_wait_all();            // stores must land before the CTA retires
     }
 
-template <int KSTEPS, int NT>     // KSTEPS = BLOCK_K / 16: 4 (128-byte swizzle) or 2 (64-byte swizzle); NT = threads per CTA
+// KSTEPS = BLOCK_K / 16: 4 (128-byte swizzle) or 2 (64-byte swizzle); NT = threads per CTA;
+// CTA2: launched as clusters of two CTAs that feed one cta_group::2 MMA (see TcParams::cta2).  Per 256 x N x 16 MMA each
+// SM then reads 4 KB of A + 16 N bytes of B from its shared memory instead of 4 KB + 32 N, and the TMA writes shrink
+// alike -- the shared-memory port was what bounded the one-CTA kernel at N >= 128 (profiles/r01_notes.md).
+template <int KSTEPS, int NT, bool CTA2>
 __global__ void __launch_bounds__(NT, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TcParams p) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents();
     if (p.dbg && threadIdx.x == 0) {       // trace mode: per-CTA entry stamp (globaltimer ns, SM clock)
         const unsigned long long g = gtimer(); const long long c = clock64();
@@ -469,6 +526,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;          // swizzle atoms need 1024-byte alignment
+    // the CTA-pair variant is sized without alignment slack (it buys the sixth stage at Cout = 512): the declared
+    // alignment of smem_raw must hold, otherwise fail loudly instead of running past the allocation
+    if (CTA2 && (raw & 1023u)) { if (p.dbg) p.dbg[0] = 99; __trap(); }
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
     const uint32_t S = (uint32_t)p.stages;
     const uint32_t out_base = sbase + S * stage_bytes;       // 8 warps x 2 staging buffers for the TMA-store epilogue
@@ -480,19 +540,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = threadIdx.x; i < p.Cout; i += NT) sbias[i] = p.bias ? p.bias[i] : 0.f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;                 // 0 = leader (issues the pair's MMAs)
+    // work items of this CTA (tiles) or of its cluster (units): first index and stride
+    const int w0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int wstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int wtotal = CTA2 ? p.num_units : p.num_tiles;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); if (p.tma_store) tma_prefetch_desc(&tmY); }
     if (warp == 1 && lane == 0) {
+        // the leader's tmem_empty barriers collect the epilogue warps of BOTH CTAs of a pair
+        const uint32_t n_epi = 4u * (uint32_t)p.csplit * (CTA2 ? 2u : 1u);
         for (uint32_t i = 0; i < S; ++i) { mbar_init(bar_base + 8u * i, 1); mbar_init(bar_base + 8u * (S + i), 1); }
-        for (uint32_t i = 0; i < 8; ++i) { mbar_init(bar_base + 8u * (2u * S + i), 1); mbar_init(bar_base + 8u * (2u * S + 8u + i), 4u * (uint32_t)p.csplit); }
+        for (uint32_t i = 0; i < 8; ++i) { mbar_init(bar_base + 8u * (2u * S + i), 1); mbar_init(bar_base + 8u * (2u * S + 8u + i), n_epi); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTA2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();    // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     pdl_wait();      // everything above overlapped the previous kernel's tail; activations are read below
@@ -511,9 +584,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t stage = 0, phase = 0;
         int tn = 0;
         TileCur tc;
-        tc.init(p, blockIdx.x + (int)pipe * gridDim.x, (int)(NP * gridDim.x));
-        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += (int)(NP * gridDim.x), tc.step(p)) {
-            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt * p.tb, n0 = tc.nt * p.block_n;
+        tc.init(p, w0 + (int)pipe * wstride, (int)NP * wstride);
+        for (int t = w0 + (int)pipe * wstride; t < wtotal; t += (int)NP * wstride, tc.step(p)) {
+            int x0, y0, b0, n0;
+            if (CTA2) {
+                const int m = 2 * (t / p.tiles_n) + (int)rank, r = m / p.tiles_x;
+                x0 = (m % p.tiles_x) * p.tw; y0 = (r % p.tiles_y) * p.th; b0 = (r / p.tiles_y) * p.tb;
+                n0 = (t % p.tiles_n) * p.block_n + (int)rank * (p.block_n >> 1);     // this CTA's half of the weight tile
+            } else {
+                x0 = tc.xt * p.tw; y0 = tc.yt * p.th; b0 = tc.bt * p.tb; n0 = tc.nt * p.block_n;
+            }
             for (int tap = 0; tap < p.taps; ++tap) {
                 int dx = 0, dy = 0, plane = 0;
                 if (p.taps == 9) {
@@ -529,12 +609,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(empty, phase ^ 1u, p.dbg, 1);
                     if (pipe == 0 && lane == 0) trace(p.dbg, 0, tn, 1);
                     if (elect_one()) {
-                        mbar_expect_tx(full, stage_bytes);
                         const uint32_t sa = sbase + gs * stage_bytes, sb = sa + p.a_bytes;
                         const int c = p.x_coff + kc * p.block_k;
-                        if (p.phase4) tma_load_5d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
-                        else tma_load_4d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0);
-                        tma_load_2d(sb, &tmB, full, tap * p.Cin + kc * p.block_k, n0);
+                        if (CTA2) {
+                            // both CTAs' boxes complete on the leader's barrier, which expects the pair's bytes
+                            if (rank == 0) mbar_expect_tx(full, 2u * stage_bytes);
+                            if (p.phase4) tma_load_5d_cg2(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
+                            else tma_load_4d_cg2(sa, &tmA, full, c, x0 + dx, y0 + dy, b0);
+                            tma_load_2d_cg2(sb, &tmB, full, tap * p.Cin + kc * p.block_k, n0);
+                        } else {
+                            mbar_expect_tx(full, stage_bytes);
+                            if (p.phase4) tma_load_5d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
+                            else tma_load_4d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0);
+                            tma_load_2d(sb, &tmB, full, tap * p.Cin + kc * p.block_k, n0);
+                        }
                     }
                     __syncwarp();
                     if (pipe == 0 && lane == 0) trace(p.dbg, 0, tn, 2);
@@ -542,19 +630,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-    } else if ((warp == 1 || warp == 3) && (uint32_t)(warp >> 1) < NP) {
-        // ================= MMA issuer (warp-uniform loop, elected lane issues) =================
+    } else if ((warp == 1 || warp == 3) && (uint32_t)(warp >> 1) < NP && rank == 0) {
+        // ================= MMA issuer (warp-uniform loop, elected lane issues; leader CTA only) =================
         const uint32_t pipe = (uint32_t)warp >> 1;
         uint32_t stage = 0, phase = 0;
         const uint64_t desc0 = make_smem_desc(0, p.sbo16, p.layout_type);
         const uint32_t desc_hi = (uint32_t)(desc0 >> 32), desc_lo0 = (uint32_t)desc0;
         const uint32_t stage16 = stage_bytes >> 4, a16 = p.a_bytes >> 4;
-        const uint32_t ring_lo = desc_lo0 + ((sbase + pipe * S2 * stage_bytes) >> 4);   // smem < 256 KB: no overflow of the 14-bit field
+        const uint32_t ring_lo = desc_lo0 + (((sbase + pipe * S2 * stage_bytes) >> 4) & 0x3FFFu);   // 14-bit start-address field (smem < 256 KB)
         int tn = 0;
         // local tile j of this CTA uses accumulator j % nacc, in phase (j / nacc) & 1
         const uint32_t NACC = (uint32_t)p.nacc;
         uint32_t acc = pipe % NACC, acc_phase = (pipe / NACC) & 1u;
-        for (int t = blockIdx.x + (int)pipe * gridDim.x; t < p.num_tiles; t += (int)(NP * gridDim.x)) {
+        for (int t = w0 + (int)pipe * wstride; t < wtotal; t += (int)NP * wstride) {
             const uint32_t tfull = bar_base + 8u * (2u * S + acc), tempty = bar_base + 8u * (2u * S + 8u + acc);
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.acc_stride;
             mbar_wait(tempty, acc_phase ^ 1u, p.dbg, 2);
@@ -568,12 +656,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 11);
                 if (elect_one()) {
                     const uint32_t a_lo = ring_lo + stage * stage16, b_lo = a_lo + a16;
-                    umma_bf16(d_tmem, a_lo, b_lo, desc_hi, p.idesc, it > 0 ? 1u : 0u);
+                    if (CTA2) {
+                        umma_bf16_cg2(d_tmem, a_lo, b_lo, desc_hi, p.idesc, it > 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 1; k < KSTEPS; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the >>4 address field
-                        umma_bf16(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, 1u);
-                    umma_commit(empty);                       // frees the smem stage when these MMAs retire
-                    if (it == kiters - 1) umma_commit(tfull); // accumulator complete -> epilogue
+                        for (int k = 1; k < KSTEPS; ++k)
+                            umma_bf16_cg2(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, 1u);
+                        umma_commit_cg2(empty);                       // frees the stage in both CTAs
+                        if (it == kiters - 1) umma_commit_cg2(tfull); // both CTAs' accumulator halves complete -> their epilogues
+                    } else {
+                        umma_bf16(d_tmem, a_lo, b_lo, desc_hi, p.idesc, it > 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 1; k < KSTEPS; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the >>4 address field
+                            umma_bf16(d_tmem, a_lo + 2u * k, b_lo + 2u * k, desc_hi, p.idesc, 1u);
+                        umma_commit(empty);                       // frees the smem stage when these MMAs retire
+                        if (it == kiters - 1) umma_commit(tfull); // accumulator complete -> epilogue
+                    }
                 }
                 __syncwarp();
                 if (pipe == 0 && lane == 0) trace(p.dbg, 1, tn, 12);
@@ -583,14 +680,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
-        epilogue_role<NT == NT_2WG>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
+        epilogue_role<NT == NT_2WG, CTA2>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
     }
 
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();    // neither CTA retires (or frees TMEM) while its peer may still signal it
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        else      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
     if (p.dbg && threadIdx.x == 0) {
         const unsigned long long g = gtimer(); const long long c = clock64();
@@ -622,7 +721,7 @@ template <int KSTEPS, int COUT>
 __global__ void __launch_bounds__(NT_3WG, 1)
 conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmY, const TcParams p) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents();
     if (p.dbg && threadIdx.x == 0) {       // trace mode: per-CTA entry stamp (globaltimer ns, SM clock)
         const unsigned long long g = gtimer(); const long long c = clock64();
@@ -755,7 +854,7 @@ template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmY, const TcParams p) {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents();
     if (p.dbg && threadIdx.x == 0) {
         const unsigned long long g = gtimer(); const long long c = clock64();
@@ -931,9 +1030,16 @@ EncodeTiledFn get_encode() {
 
 int* g_trace_buf = nullptr;
 
+// Tuning knobs (YRE_TC_*) exist only in builds made with -DYRE_TUNING (YRE_TUNING=1 python yolo-re_b200/build.py);
+// the product build reads no environment variables.
 int env_int(const char* name, int dflt) {
+#ifdef YRE_TUNING
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
 }
 
 }  // namespace
@@ -950,10 +1056,19 @@ static cudaError_t launch_tc(K kernel, int grid, int block, size_t smem, cudaStr
     static const int pdl = env_int("YRE_TC_PDL", 1);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int n = 0;
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (pl->p.cta2) {                     // CTA pairs: clusters of two (always on one TPC)
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = 2; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    cfg.attrs = at; cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, pl->tmA, pl->tmB, pl->tmY, pl->p);
 }
 
@@ -1042,12 +1157,16 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     p.mtiles = (int)mtiles;
     p.upn = (int)((mtiles + p.npair - 1) / p.npair);
     p.num_units = p.upn * p.tiles_n;
+    // CTA pairs for the wide N tiles of the generic kernel (its shared-memory port bound: 4 KB + 32 N bytes read and as
+    // many written per 128 x N x 16 MMA; a pair halves the weight half of both)
+    p.cta2 = (!p.halo && bn >= 128 && mtiles >= 2 && env_int("YRE_TC_CTA2", 1) != 0) ? 1 : 0;
+    if (p.cta2) p.num_units = (int)((mtiles + 1) / 2) * p.tiles_n;
     p.a_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
     if (p.halo) {
         p.halo_tx = (uint32_t)(10 * 18 * p.block_k * 2);
         p.a_bytes = (p.halo_tx + 1023u) & ~1023u;
     }
-    p.b_bytes = (uint32_t)(bn * p.block_k * 2);
+    p.b_bytes = (uint32_t)((p.cta2 ? bn / 2 : bn) * p.block_k * 2);       // a pair's CTA stages half of the weight tile
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
     // bf16 outputs leave through a swizzled staging tile + TMA store; fp32 outputs (raw head logits) store directly
     p.tma_store = (d.y.dtype == YRE_BF16 && bn % 32 == 0 && env_int("YRE_TC_DIRECT_STORE", 0) == 0) ? 1 : 0;
@@ -1064,6 +1183,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     // where TMEM only holds 2-3 buffers, split the chunks of each tile over the warpgroups instead.
     p.nthreads = bn <= 64 ? NT_3WG : NT_2WG;
     { const int f = env_int("YRE_TC_THREADS", 0); if ((f == NT_2WG || f == NT_3WG) && p.halo != 1) p.nthreads = f; }
+    if (p.cta2) p.nthreads = NT_2WG;
     const int maxg = (p.nthreads / 32 - 4) / 4;
     if (bn <= 64)       { p.acc_stride = 64;  p.nacc = 6; p.tgroups = maxg; p.csplit = 1; }
     else if (bn <= 128) { p.acc_stride = 128; p.nacc = 4; p.tgroups = 2; p.csplit = 1; }
@@ -1075,7 +1195,8 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     while (p.csplit > 1 && p.csplit > (bn + 31) / 32) --p.csplit;   // every warpgroup owns at least one chunk
     p.ngroups = p.tgroups * p.csplit;
     const uint32_t n_stage_bufs = 8u * (uint32_t)p.ngroups;         // 4 warps x 2 buffers per group
-    const uint32_t smem_cap = 227u * 1024u - 1024u - 256u - (uint32_t)Cout * 4u;   // alignment slack + barriers + bias copy
+    const uint32_t align_slack = p.cta2 ? 0u : 1024u;      // the pair kernel relies on (and checks) the declared 1024-byte alignment
+    const uint32_t smem_cap = 227u * 1024u - align_slack - 256u - (uint32_t)Cout * 4u;   // alignment slack + barriers + bias copy
     int stages = (int)((smem_cap - n_stage_bufs * p.stage_out_bytes) / stage_bytes);
     if (p.halo == 1) stages = (int)((smem_cap - n_stage_bufs * p.stage_out_bytes - 9u * p.b_bytes) / p.a_bytes);
     if (stages > 8) stages = 8;
@@ -1104,10 +1225,10 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     { const int f = env_int("YRE_TC_PIPES", 0); if (f >= 1 && f <= 2 && p.nacc % f == 0 && stages >= 2 * f) p.npipes = f; }
     if (p.npipes == 2 || p.halo == 1) stages &= ~1;
     p.stages = stages;
-    pl->smem = (size_t)stages * stage_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 16) + 32 + (size_t)Cout * 4 + 1024;
+    pl->smem = (size_t)stages * stage_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 16) + 32 + (size_t)Cout * 4 + align_slack;
     if (p.halo == 2) pl->smem = (size_t)stages * p.npair * p.a_bytes + (size_t)p.stages_b * p.tps * p.b_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 2 * p.stages_b + 16) + 32 + (size_t)Cout * 4 + 1024;
     else if (p.halo) pl->smem = 9 * (size_t)p.b_bytes + (size_t)stages * p.a_bytes + n_stage_bufs * p.stage_out_bytes + 8 * (2 * stages + 18) + 32 + (size_t)Cout * 4 + 1024;
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((p.cta2 ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
     p.bias = d.bias; p.act = d.act;
     p.y = d.y.ptr; p.y_f32 = d.y.dtype == YRE_F32; p.y_ctot = d.y.C_total; p.y_coff = d.y.c_off;
     p.res = d.res.ptr; p.res_f32 = d.res.ptr ? d.res.dtype == YRE_F32 : 0;
@@ -1122,6 +1243,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     }
     pl->grid = p.num_tiles < sms ? p.num_tiles : sms;
     if (p.halo == 2) pl->grid = p.num_units < sms ? p.num_units : sms;
+    if (p.cta2) pl->grid = 2 * (p.num_units < sms / 2 ? p.num_units : sms / 2);
 
     // ---- tensor maps ----
     const CUtensorMapSwizzle swz = p.block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1148,7 +1270,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         const cuuint64_t K = (cuuint64_t)p.taps * Cin;
         cuuint64_t gdim[2] = {K, (cuuint64_t)Cout};
         cuuint64_t gstr[1] = {K * 2};
-        cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)bn};
+        cuuint32_t box[2] = {(cuuint32_t)p.block_k, (cuuint32_t)(p.cta2 ? bn / 2 : bn)};
         cuuint32_t est[2] = {1, 1};
         r = enc(&pl->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d.w), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1169,37 +1291,36 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     return YRE_OK;
 }
 
+template <typename K> static int opt_in_smem(K kernel) {
+    YRE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return YRE_OK;
+}
+
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4, NT_2WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, NT_2WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<4, NT_3WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        YRE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, NT_3WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    static YrePerDeviceOnce once;
+    if (int e = once.run([]() -> int {
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_3WG, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_3WG, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, true>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, true>)) return r;
+            if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_2WG>)) return r;
+            if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_3WG>)) return r;
+            if (int r = opt_in_smem(conv3_halo_kernel<4, 64>)) return r;
+            if (int r = opt_in_smem(conv3_halo_kernel<4, 32>)) return r;
+            if (int r = opt_in_smem(conv3_halo_kernel<2, 64>)) return r;
+            if (int r = opt_in_smem(conv3_halo_kernel<2, 32>)) return r;
+            return YRE_OK;
+        })) return e;
     const bool k64 = pl->p.block_k == 64;
     if (pl->p.halo == 2) {
-        static bool sattr_done = false;
-        if (!sattr_done) {
-            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_stream_kernel<NT_2WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_stream_kernel<NT_3WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            sattr_done = true;
-        }
         if (pl->p.nthreads == NT_3WG) YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_3WG>, pl->grid, NT_3WG, pl->smem, s, pl));
         else                          YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_2WG>, pl->grid, NT_2WG, pl->smem, s, pl));
         YRE_LAUNCH_CHECK("conv3_halo_stream");
         return YRE_OK;
     }
     if (pl->p.halo) {
-        static bool hattr_done = false;
-        if (!hattr_done) {
-            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            YRE_CUDA(cudaFuncSetAttribute(conv3_halo_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            hattr_done = true;
-        }
         const bool c64 = pl->p.Cout == 64;
         if (k64) { if (c64) YRE_CUDA(launch_tc(conv3_halo_kernel<4, 64>, pl->grid, NT_3WG, pl->smem, s, pl));
                    else     YRE_CUDA(launch_tc(conv3_halo_kernel<4, 32>, pl->grid, NT_3WG, pl->smem, s, pl)); }
@@ -1208,12 +1329,18 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
         YRE_LAUNCH_CHECK("conv3_halo");
         return YRE_OK;
     }
+    if (pl->p.cta2) {                     // N tiles >= 128 only, which always run the two-warpgroup epilogue
+        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+        YRE_LAUNCH_CHECK("conv_tc (CTA pair)");
+        return YRE_OK;
+    }
     if (pl->p.nthreads == NT_3WG) {
-        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_3WG>, pl->grid, NT_3WG, pl->smem, s, pl));
-        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_3WG>, pl->grid, NT_3WG, pl->smem, s, pl));
+        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_3WG, false>, pl->grid, NT_3WG, pl->smem, s, pl));
+        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_3WG, false>, pl->grid, NT_3WG, pl->smem, s, pl));
     } else {
-        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG>, pl->grid, NT_2WG, pl->smem, s, pl));
-        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG>, pl->grid, NT_2WG, pl->smem, s, pl));
+        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, false>, pl->grid, NT_2WG, pl->smem, s, pl));
+        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, false>, pl->grid, NT_2WG, pl->smem, s, pl));
     }
     YRE_LAUNCH_CHECK("conv_tc");
     return YRE_OK;
@@ -1231,10 +1358,13 @@ int conv_tc_rebind(ConvTcPlan* pl, const void* old_ptr, void* new_ptr) {
     return n;
 }
 
-// debugging aid: copies the last trace buffer (8192 ints) to the host; returns 0 when tracing is off
+#ifdef YRE_TUNING
+// debugging aid of tuning builds (not part of include/yre.h): copies the last trace buffer (8192 ints) to the host;
+// returns 0 when tracing is off
 extern "C" int yre_debug_read_trace(int* host, int n) {
     if (!g_trace_buf) return 0;
     cudaDeviceSynchronize();
     cudaMemcpy(host, g_trace_buf, sizeof(int) * (n < 8192 ? n : 8192), cudaMemcpyDeviceToHost);
     return n < 8192 ? n : 8192;
 }
+#endif

@@ -159,6 +159,7 @@ struct SelectParams {
     NmsWs ws;
     float* out; int* counts; long long* keep_anchor;
     int keys_in_smem;     // SMEM_KEYS or 0
+    const float* scale;   // optional [B][5] = pad_w, pad_h, gain, orig_w, orig_h (scale_boxes fused into the output)
 };
 
 __device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const float4 b, const float ab, const double thr) {
@@ -312,7 +313,15 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
             const int i = kpos[q], k = kept + q;
             kbox[k] = cbox[i]; karea[k] = carea[i];
             float* o = p.out + ((size_t)b * p.max_det + k) * 6;
-            const float4 u = ubox[i];
+            float4 u = ubox[i];
+            if (p.scale) {        // scale_boxes (scripts/detect.py:74-109), same ops as scale_boxes_kernel (k_preproc.cu)
+                const float* sc = p.scale + (size_t)b * 5;
+                const float pw = sc[0], ph = sc[1], gain = sc[2], ow = sc[3], oh = sc[4];
+                u.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(u.x, pw), gain), 0.f), ow);
+                u.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(u.y, ph), gain), 0.f), oh);
+                u.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(u.z, pw), gain), 0.f), ow);
+                u.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(u.w, ph), gain), 0.f), oh);
+            }
             o[0] = u.x; o[1] = u.y; o[2] = u.z; o[3] = u.w; o[4] = cconf[i]; o[5] = __int2float_rn(ccls[i]);
             p.keep_anchor[(size_t)b * p.max_det + k] = canc[i];
         }
@@ -345,16 +354,19 @@ extern "C" size_t yre_nms_workspace_bytes(int32_t B, int32_t A) {
     return sizeof(u64) * (size_t)B * pow2ceil(A) + sizeof(int) * (size_t)B * A + 2 * sizeof(int) * (size_t)B + 256;
 }
 
-int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
-    if (!d.pred || !d.out || !d.counts || !d.keep_anchor || !d.workspace) YRE_FAIL(YRE_EINVAL, "nms: null pointer");
+static int check_nms(const yre_nms_desc& d, bool outputs) {
+    if (!d.pred || !d.workspace) YRE_FAIL(YRE_EINVAL, "nms: null pointer");
+    if (outputs && (!d.out || !d.counts || !d.keep_anchor)) YRE_FAIL(YRE_EINVAL, "nms: null output pointer");
     if (d.B <= 0 || d.A <= 0 || d.nc <= 0) YRE_FAIL(YRE_EINVAL, "nms: bad extent B=%d A=%d nc=%d", d.B, d.A, d.nc);
     if (d.max_det <= 0 || d.max_det > 4096) YRE_FAIL(YRE_EUNSUPPORTED, "nms: max_det=%d (supported 1..4096)", d.max_det);
     if (d.workspace_bytes < yre_nms_workspace_bytes(d.B, d.A)) YRE_FAIL(YRE_EINVAL, "nms: workspace too small");
     if (d.n_classes > 0 && !d.classes) YRE_FAIL(YRE_EINVAL, "nms: classes pointer missing");
     if ((reinterpret_cast<uintptr_t>(d.pred) & 15) || (reinterpret_cast<uintptr_t>(d.workspace) & 15))
         YRE_FAIL(YRE_EINVAL, "nms: pred/workspace must be 16-byte aligned");
-    NmsWs ws = carve(d.workspace, d.B, d.A);
+    return YRE_OK;
+}
 
+static int launch_nms_filter(const yre_nms_desc& d, const NmsWs& ws, cudaStream_t s) {
     nms_init_kernel<<<yre_cdiv(d.B, 256), 256, 0, s>>>(ws.count, ws.maxc, d.B);
     YRE_LAUNCH_CHECK("nms_init");
 
@@ -368,18 +380,32 @@ int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
     const int tiles = yre_cdiv(d.A, 32) * d.B;
     nms_filter_kernel<<<yre_cdiv(tiles, warps), warps * 32, per_warp * warps, s>>>(fp);
     YRE_LAUNCH_CHECK("nms_filter");
+    return YRE_OK;
+}
+
+extern "C" int yre_nms_filter_only(const yre_nms_desc* d, yre_stream_t s) {
+    if (!d) YRE_FAIL(YRE_EINVAL, "nms: null descriptor");
+    if (int e = check_nms(*d, false)) return e;
+    return launch_nms_filter(*d, carve(d->workspace, d->B, d->A), (cudaStream_t)s);
+}
+
+int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
+    if (int e = check_nms(d, true)) return e;
+    NmsWs ws = carve(d.workspace, d.B, d.A);
+    if (int e = launch_nms_filter(d, ws, s)) return e;
 
     SelectParams sp;
     sp.pred = d.pred; sp.B = d.B; sp.A = d.A; sp.nc = d.nc; sp.iou = d.iou_thres; sp.max_det = d.max_det;
     sp.agnostic = d.agnostic; sp.ws = ws; sp.out = d.out; sp.counts = d.counts;
     sp.keep_anchor = reinterpret_cast<long long*>(d.keep_anchor);
     sp.keys_in_smem = SMEM_KEYS;
+    sp.scale = d.scale;
     const size_t smem = select_smem_bytes(d.max_det, SMEM_KEYS);
-    static bool attr_done = false;
-    if (!attr_done) {
-        YRE_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
-    }
+    static YrePerDeviceOnce once;
+    if (int e = once.run([]() -> int {
+            YRE_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            return YRE_OK;
+        })) return e;
     if (smem > 200 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "nms: shared memory budget exceeded");
     nms_select_kernel<<<d.B, CHUNK, smem, s>>>(sp);
     YRE_LAUNCH_CHECK("nms_select");

@@ -632,12 +632,12 @@ int launch_spp_maxpool(const yre_view& x, const yre_view& y5, const yre_view& y9
         if (x.C % c == 0 && (size_t)2 * x.H * x.W * c * sizeof(float) <= 96 * 1024) { chk = c; break; }
     if (chk) {
         const size_t smem = (size_t)2 * x.H * x.W * chk * sizeof(float);
-        static bool attr_done = false;
-        if (!attr_done) {
-            YRE_CUDA(cudaFuncSetAttribute(spp_plane_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            YRE_CUDA(cudaFuncSetAttribute(spp_plane_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr_done = true;
-        }
+        static YrePerDeviceOnce once;        // the opt-in is per device
+        if (int e = once.run([]() -> int {
+                YRE_CUDA(cudaFuncSetAttribute(spp_plane_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                YRE_CUDA(cudaFuncSetAttribute(spp_plane_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                return YRE_OK;
+            })) return e;
         dim3 pg((unsigned)x.B, (unsigned)(x.C / chk));
         if (x.dtype == YRE_F32) spp_plane_kernel<float><<<pg, 256, smem, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13), chk);
         else spp_plane_kernel<__nv_bfloat16><<<pg, 256, smem, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13), chk);

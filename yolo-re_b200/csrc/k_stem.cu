@@ -17,6 +17,7 @@ namespace {
 
 struct StemParams {
     const float* x;
+    const uint8_t* xu8;  // non-null: uint8 [B][H][W][3] frames in BGR order (cv2 layout); value / 255 and BGR->RGB fused
     DView y;
     const float* w;     // [Cout][3][3][Cin]
     const float* bias;
@@ -25,7 +26,7 @@ struct StemParams {
 
 constexpr int PX = 4;   // output pixels per thread (consecutive in x): weights are read once per 4 pixels
 
-template <typename TOut, int CIN, int STRIDE>
+template <typename TOut, int CIN, int STRIDE, bool U8 = false>
 __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
     extern __shared__ __align__(16) float sw[];               // [9*CIN][Cout] + bias[Cout]
     constexpr int K = 9 * CIN;
@@ -56,8 +57,12 @@ __global__ void __launch_bounds__(128) stem_kernel(const StemParams p) {
             const int ix = ox0 * STRIDE + cx - 1;
             const bool ok = rok && ix >= 0 && ix < p.W;
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci)
-                in[dy][cx][ci] = ok ? __ldg(p.x + (((long long)b * CIN + ci) * p.H + iy) * p.W + ix) : 0.f;
+            for (int ci = 0; ci < CIN; ++ci) {
+                if (U8)      // model channel ci (RGB) is byte 2 - ci of the BGR pixel; float(u8) / 255 as scripts/detect.py:226
+                    in[dy][cx][ci] = ok ? __fdiv_rn((float)__ldg(p.xu8 + (((long long)b * p.H + iy) * p.W + ix) * 3 + (2 - ci)), 255.f) : 0.f;
+                else
+                    in[dy][cx][ci] = ok ? __ldg(p.x + (((long long)b * CIN + ci) * p.H + iy) * p.W + ix) : 0.f;
+            }
         }
     }
 
@@ -415,10 +420,162 @@ __global__ void __launch_bounds__(128, MINB) stem_mma_s2v_kernel(const StemParam
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+
+// Stride-2 product kernel fed straight from uint8 HWC BGR camera frames (W % 16 == 0, Cin == 3): what
+// scripts/detect.py:223-227 does on the host -- BGR->RGB, HWC->CHW, .float() / 255 -- happens in the gather, so the fp32
+// image tensor never exists (12 bytes/pixel written by K8 and read back here become 3 bytes/pixel read once).
+// A segment's three input rows are three 128-byte windows [96 seg - 16, 96 seg + 112) of the frame rows: 24 aligned
+// 16-byte cp.async copies per segment instead of 90 (chunks outside the row are zero-filled = conv padding, the value
+// of a padded pixel being 0 after the division as well).  im2col element (pixel m, tap (dy,dx), model channel ci) is
+// byte dy*128 + 6m + 3dx + (2 - ci) + 13 of the stage.  bf16(float(v) * (1/255)) equals bf16(float(v) / 255) for all
+// 256 byte values (checked exhaustively, tests/test_cpu_host.py), so the A fragments are bit-identical to the ones the
+// fp32-tensor path builds and so is the output.  float(v) is built as (0x4B000000 | v) - 2^23: no I2F on the MUFU pipe.
+template <int NST, int MINB>
+__global__ void __launch_bounds__(128, MINB) stem_mma_s2u8_kernel(const StemParams p, int segs, long long total_tiles) {
+    constexpr int ROWB = 128, ZERO = 3 * ROWB, STAGE = 3 * ROWB + 16;     // bytes; the 16 bytes at ZERO stay 0 (K padding)
+    __shared__ __align__(16) uint8_t sin_all[4][NST * STAGE];
+    __shared__ __align__(16) __nv_bfloat16 sout_all[4][16][64 + 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    uint8_t* sin = sin_all[warp];
+    __nv_bfloat16 (*sout)[72] = sout_all[warp];
+    constexpr int K = 27;
+    for (int i = lane; i < NST * STAGE / 4; i += 32) reinterpret_cast<uint32_t*>(sin)[i] = 0u;
+
+    uint32_t bfrag[2][8][2];
+    float2 bias2[8];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int n = j * 8 + g, k0 = ks * 16 + 2 * t + 8 * h;
+                const float w0 = k0 < K ? p.w[n * K + k0] : 0.f, w1 = (k0 + 1) < K ? p.w[n * K + k0 + 1] : 0.f;
+                bfrag[ks][j][h] = pack_bf16x2(w0, w1);
+            }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        bias2[j] = make_float2(p.bias ? p.bias[j * 8 + 2 * t] : 0.f, p.bias ? p.bias[j * 8 + 2 * t + 1] : 0.f);
+    // byte (inside a stage) of im2col element (pixel m, k = tap * 3 + ci); K padding -> a zero byte
+    int ao[2][2][2][2];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = ks * 16 + 2 * t + 8 * h + e;
+                if (k < K) {
+                    const int tap = k / 3, ci = k % 3, dy = tap / 3, dx = tap % 3;
+                    const int o = dy * ROWB + 3 * dx + (2 - ci) + 13;
+                    ao[ks][h][e][0] = o + 6 * g; ao[ks][h][e][1] = o + 6 * (g + 8);
+                } else ao[ks][h][e][0] = ao[ks][h][e][1] = ZERO;
+            }
+    // this lane's 16-byte copy of a segment: row dy = lane / 8, chunk lane % 8 (lanes 24..31 copy nothing)
+    const bool g_ok = lane < 24;
+    const int g_dy = lane >> 3, g_c16 = lane & 7;
+    const long long rowb = (long long)p.W * 3;
+    const uint32_t g_so = (uint32_t)__cvta_generic_to_shared(sin) + (uint32_t)(g_dy * ROWB + 16 * g_c16);
+    const bool ph4 = p.y.layout == YRE_PHASE4;
+    const long long plane = (long long)p.y.B * p.y.Hp * p.y.Wp * p.y.C_total;
+    int o_off[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = lane + 32 * q, px = i >> 3, c16 = i & 7;
+        o_off[q] = (ph4 ? (px >> 1) : px) * p.y.C_total + c16 * 8;
+    }
+
+    const int wstride = (int)gridDim.x * 4;
+    const int d_seg = wstride % segs, d_oy = (wstride / segs) % p.Ho, d_b = (wstride / segs) / p.Ho;
+    int tile = (int)blockIdx.x * 4 + warp;
+    int seg = tile % segs, oy = (tile / segs) % p.Ho, b = (tile / segs) / p.Ho;
+    int ftile = tile, fseg = seg, foy = oy, fb = b, fstage = 0, cstage = 0;
+    const int ntiles = (int)total_tiles;
+
+    auto issue = [&]() {
+        if (ftile < ntiles) {
+            const int iy = 2 * foy + g_dy - 1;
+            const long long xb = 96ll * fseg - 16 + 16 * g_c16;             // first byte of the chunk inside its frame row
+            const bool in = iy >= 0 && iy < p.H && xb >= 0 && xb < rowb;     // rowb % 16 == 0: a chunk is inside or outside
+            if (g_ok) {
+                const uint8_t* src = in ? p.xu8 + ((long long)fb * p.H + iy) * rowb + xb : p.xu8;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(g_so + (uint32_t)(fstage * STAGE)), "l"(src), "r"(in ? 16 : 0) : "memory");
+            }
+            fseg += d_seg; int cy = fseg >= segs; fseg -= cy ? segs : 0;
+            foy += d_oy + cy; cy = foy >= p.Ho; foy -= cy ? p.Ho : 0;
+            fb += d_b + cy;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        ftile += wstride;
+        if (++fstage == NST) fstage = 0;
+    };
+    // float(byte) * (1/255): (0x4B000000 | v) is the float 2^23 + v, the subtraction is exact, one rounding in the product
+    auto cvt = [](uint8_t v) { return __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)v), 8388608.f), 1.0f / 255.0f); };
+
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NST - 1; ++i) issue();
+    for (; tile < ntiles; tile += wstride) {
+        const int ox0 = seg * SM_PX, cb = b, coy = oy;
+        issue();
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
+        __syncwarp();
+        const uint8_t* st = sin + cstage * STAGE;
+        seg += d_seg; int cy = seg >= segs; seg -= cy ? segs : 0;
+        oy += d_oy + cy; cy = oy >= p.Ho; oy -= cy ? p.Ho : 0;
+        b += d_b + cy;
+
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j][0] = bias2[j].x; acc[j][1] = bias2[j].y; acc[j][2] = bias2[j].x; acc[j][3] = bias2[j].y; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t a[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                a[2 * h + 0] = pack_bf16x2(cvt(st[ao[ks][h][0][0]]), cvt(st[ao[ks][h][1][0]]));     // row g
+                a[2 * h + 1] = pack_bf16x2(cvt(st[ao[ks][h][0][1]]), cvt(st[ao[ks][h][1][1]]));     // row g + 8
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mma_bf16_16816(acc[j], a, bfrag[ks][j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float2 lo = make_float2(acc[j][0], acc[j][1]), hi = make_float2(acc[j][2], acc[j][3]);
+            if (p.act == YRE_ACT_SILU) {
+                const float2 hl = __fmul2_rn(lo, make_float2(0.5f, 0.5f)), hh = __fmul2_rn(hi, make_float2(0.5f, 0.5f));
+                float2 tl, th;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tl.x) : "f"(hl.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(tl.y) : "f"(hl.y));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(hh.x));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(hh.y));
+                lo = __ffma2_rn(hl, tl, hl); hi = __ffma2_rn(hh, th, hh);
+            }
+            *reinterpret_cast<uint32_t*>(&sout[g][j * 8 + 2 * t]) = pack_bf16x2(lo.x, lo.y);
+            *reinterpret_cast<uint32_t*>(&sout[g + 8][j * 8 + 2 * t]) = pack_bf16x2(hi.x, hi.y);
+        }
+        __syncwarp();
+        const long long ybase = ph4
+            ? ((((long long)((coy & 1) * 2) * p.y.B + cb) * p.y.Hp + (coy >> 1)) * p.y.Wp + (ox0 >> 1)) * p.y.C_total + p.y.c_off
+            : (((long long)cb * p.y.H + coy) * p.y.W + ox0) * p.y.C_total + p.y.c_off;
+        __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y.ptr) + ybase;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = lane + 32 * q, px = i >> 3, c16 = i & 7;
+            if (ox0 + px < p.Wo)
+                *reinterpret_cast<uint4*>(yb + o_off[q] + ((ph4 && (px & 1)) ? plane : 0ll)) = *reinterpret_cast<const uint4*>(&sout[px][c16 * 8]);
+        }
+        if (++cstage == NST) cstage = 0;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 }  // namespace
 
 int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
-    if (!d.x_nchw || !d.w) YRE_FAIL(YRE_EINVAL, "stem: null pointer");
+    const bool u8 = d.x_u8_hwc != nullptr;
+    if ((!d.x_nchw && !u8) || !d.w) YRE_FAIL(YRE_EINVAL, "stem: null pointer");
+    if (u8 && d.Cin != 3) YRE_FAIL(YRE_EUNSUPPORTED, "stem: uint8 HWC frames need Cin == 3 (got %d)", d.Cin);
     if (yre_check_view(&d.y, "stem.y")) return YRE_EINVAL;
     if (d.Cin < 1 || d.Cin > 4) YRE_FAIL(YRE_EUNSUPPORTED, "stem: Cin=%d (supported 1..4)", d.Cin);
     if (d.stride != 1 && d.stride != 2) YRE_FAIL(YRE_EUNSUPPORTED, "stem: stride %d", d.stride);
@@ -426,9 +583,10 @@ int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
     const int Ho = (d.H + 2 - 3) / d.stride + 1, Wo = (d.W + 2 - 3) / d.stride + 1;
     if (Ho != d.y.H || Wo != d.y.W || d.B != d.y.B) YRE_FAIL(YRE_EINVAL, "stem: output extent mismatch");
     StemParams p;
-    p.x = d.x_nchw; p.y = make_dview(d.y); p.w = d.w; p.bias = d.bias;
+    p.x = d.x_nchw; p.xu8 = d.x_u8_hwc; p.y = make_dview(d.y); p.w = d.w; p.bias = d.bias;
     p.B = d.B; p.Cin = d.Cin; p.H = d.H; p.W = d.W; p.Ho = Ho; p.Wo = Wo; p.Cout = d.y.C; p.stride = d.stride; p.act = d.act;
-    if (d.y.dtype == YRE_BF16 && d.Cin <= 3 && d.y.C == 64 && (reinterpret_cast<uintptr_t>(d.y.ptr) & 15) == 0) {
+    if (u8 && d.y.dtype == YRE_BF16 && d.y.C == 64 && d.stride == 2 && d.W % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(d.y.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.x_u8_hwc) & 15) == 0) {
         const int segs = yre_cdiv(Wo, SM_PX);
         const long long tiles = (long long)d.B * Ho * segs;
         int dev = 0, sms = 148;
@@ -436,8 +594,22 @@ int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long want = (tiles + 3) / 4;
         const unsigned grid = (unsigned)(want < (long long)sms * 4 ? want : (long long)sms * 4);
-        const bool vec = d.stride == 2 && d.W % 4 == 0 && (reinterpret_cast<uintptr_t>(d.x_nchw) & 15) == 0 &&
-                         (!getenv("YRE_STEM_VEC") || atoi(getenv("YRE_STEM_VEC")) != 0);
+        stem_mma_s2u8_kernel<3, 3><<<grid, 128, 0, s>>>(p, segs, tiles);
+        YRE_LAUNCH_CHECK("stem_mma_u8");
+        return YRE_OK;
+    }
+    if (!u8 && d.y.dtype == YRE_BF16 && d.Cin <= 3 && d.y.C == 64 && (reinterpret_cast<uintptr_t>(d.y.ptr) & 15) == 0) {
+        const int segs = yre_cdiv(Wo, SM_PX);
+        const long long tiles = (long long)d.B * Ho * segs;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long want = (tiles + 3) / 4;
+        const unsigned grid = (unsigned)(want < (long long)sms * 4 ? want : (long long)sms * 4);
+        bool vec = d.stride == 2 && d.W % 4 == 0 && (reinterpret_cast<uintptr_t>(d.x_nchw) & 15) == 0;
+#ifdef YRE_TUNING
+        if (getenv("YRE_STEM_VEC") && atoi(getenv("YRE_STEM_VEC")) == 0) vec = false;
+#endif
         if (vec) stem_mma_s2v_kernel<3, 3><<<grid, 128, 0, s>>>(p, segs, tiles);   // 4 stages or 4 CTAs/SM (128 regs, spills) measured no better
         else if (d.stride == 2) stem_mma_kernel<2><<<grid, 128, 0, s>>>(p, segs, tiles);
         else stem_mma_kernel<1><<<grid, 128, 0, s>>>(p, segs, tiles);
@@ -450,7 +622,10 @@ int launch_stem(const yre_stem_desc& d, cudaStream_t s) {
     dim3 grid(yre_cdiv(total, 128));
 #define STEM_GO(T, C) do { if (d.stride == 2) stem_kernel<T, C, 2><<<grid, 128, smem, s>>>(p); else stem_kernel<T, C, 1><<<grid, 128, smem, s>>>(p); } while (0)
 #define STEM_T(T) switch (d.Cin) { case 1: STEM_GO(T, 1); break; case 2: STEM_GO(T, 2); break; case 3: STEM_GO(T, 3); break; default: STEM_GO(T, 4); }
-    if (d.y.dtype == YRE_F32) { STEM_T(float) } else { STEM_T(__nv_bfloat16) }
+#define STEM_U8(T) do { if (d.stride == 2) stem_kernel<T, 3, 2, true><<<grid, 128, smem, s>>>(p); else stem_kernel<T, 3, 1, true><<<grid, 128, smem, s>>>(p); } while (0)
+    if (u8) { if (d.y.dtype == YRE_F32) STEM_U8(float); else STEM_U8(__nv_bfloat16); }
+    else if (d.y.dtype == YRE_F32) { STEM_T(float) } else { STEM_T(__nv_bfloat16) }
+#undef STEM_U8
 #undef STEM_T
 #undef STEM_GO
     YRE_LAUNCH_CHECK("stem");

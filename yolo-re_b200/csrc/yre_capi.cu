@@ -274,6 +274,7 @@ int yre_plan_rebind(yre_plan* p, const void* old_ptr, void* new_ptr) {
                 break;
             case OP_STEM:
                 if (o.stem.x_nchw == old_ptr) { o.stem.x_nchw = (const float*)new_ptr; ++n; }
+                if (o.stem.x_u8_hwc == old_ptr) { o.stem.x_u8_hwc = (const uint8_t*)new_ptr; ++n; }
                 fix(o.stem.y.ptr);
                 break;
             case OP_DECODE:

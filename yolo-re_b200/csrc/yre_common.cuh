@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
 #include "../../include/yre.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -29,6 +31,23 @@ static inline int yre_check_view(const yre_view* v, const char* what) {
 }
 
 static inline int yre_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) are PER DEVICE: run `f` once for every device
+// ordinal a kernel family is launched on (a process may use cuda:0 and then cuda:1), thread-safe.
+struct YrePerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    std::mutex mu;
+    template <typename F> int run(F&& f) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return f();
+        if ((done.load(std::memory_order_acquire) >> dev) & 1ull) return YRE_OK;
+        std::lock_guard<std::mutex> g(mu);
+        if ((done.load(std::memory_order_relaxed) >> dev) & 1ull) return YRE_OK;
+        const int e = f();
+        if (e == YRE_OK) done.fetch_or(1ull << dev, std::memory_order_release);
+        return e;
+    }
+};
 
 // ---- device-side view addressing ----------------------------------------------------------------
 struct DView {

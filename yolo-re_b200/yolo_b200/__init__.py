@@ -6,11 +6,11 @@ Public names mirror the reference package (src/yolo/__init__.py:3-20) for the pa
 from ._lib import YreError, lib
 from .engine import precision
 from .model import BLOCKS, YOLO, ModelConfig, build_layers, parse_yaml
-from .nms import nms_raw, non_max_suppression
-from .preprocess import letterbox, preprocess, scale_boxes
+from .nms import PendingDetections, nms_raw, non_max_suppression, non_max_suppression_async
+from .preprocess import letterbox, preprocess, scale_boxes, scale_rows
 from .checkpoint import convert_upstream_state_dict, load_checkpoint
 from .metrics import DetectionAccumulator, Evaluator, compute_map, match_detections
 
-__version__ = "0.1.0"
-__all__ = ["YOLO", "non_max_suppression", "nms_raw", "precision", "YreError", "lib", "ModelConfig", "parse_yaml",
+__version__ = "0.2.0"
+__all__ = ["YOLO", "non_max_suppression", "non_max_suppression_async", "PendingDetections", "scale_rows", "nms_raw", "precision", "YreError", "lib", "ModelConfig", "parse_yaml",
            "build_layers", "BLOCKS", "letterbox", "preprocess", "scale_boxes", "convert_upstream_state_dict", "load_checkpoint", "compute_map", "match_detections", "DetectionAccumulator", "Evaluator"]

@@ -29,7 +29,8 @@ class ConvDesc(C.Structure):
 
 class StemDesc(C.Structure):
     _fields_ = [("x_nchw", C.c_void_p), ("B", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("y", View), ("w", C.c_void_p), ("bias", C.c_void_p), ("stride", C.c_int32), ("act", C.c_int32)]
+                ("y", View), ("w", C.c_void_p), ("bias", C.c_void_p), ("stride", C.c_int32), ("act", C.c_int32),
+                ("x_u8_hwc", C.c_void_p)]
 
 
 class DecodeDesc(C.Structure):
@@ -42,7 +43,7 @@ class NmsDesc(C.Structure):
                 ("conf_thres", C.c_float), ("iou_thres", C.c_double), ("max_det", C.c_int32),
                 ("classes", C.c_void_p), ("n_classes", C.c_int32), ("agnostic", C.c_int32),
                 ("out", C.c_void_p), ("counts", C.c_void_p), ("keep_anchor", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("scale", C.c_void_p)]
 
 
 class LetterboxDesc(C.Structure):
@@ -75,6 +76,7 @@ SYMBOLS = {
     "yre_dfl_decode_score": (C.c_int, [C.POINTER(DecodeDesc), C.c_void_p]),
     "yre_nms_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "yre_nms_batched": (C.c_int, [C.POINTER(NmsDesc), C.c_void_p]),
+    "yre_nms_filter_only": (C.c_int, [C.POINTER(NmsDesc), C.c_void_p]),
     "yre_letterbox_geometry": (C.c_int, [C.POINTER(LetterboxDesc), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "yre_letterbox_u8": (C.c_int, [C.POINTER(LetterboxDesc), C.c_void_p]),
     "yre_letterbox_u8_batch": (C.c_int, [C.POINTER(LetterboxDesc), C.c_int32, C.c_void_p]),

@@ -186,17 +186,23 @@ class Plan:
         assert len({(f[2], f[3], f[4]) for f in fs}) == 1
         return self.conv(x, torch.cat([f[0] for f in fs]), torch.cat([f[1] for f in fs]), fs[0][2], fs[0][3], fs[0][4], out)
 
-    def stem(self, m: B.Conv, x_nchw: torch.Tensor, phase4: bool) -> V:
+    def stem(self, m: B.Conv, x: torch.Tensor, phase4: bool) -> V:
+        """x: the fp32 NCHW image batch, or uint8 [B,H,W,3] BGR frames (BGR->RGB, HWC->CHW and /255 of
+        scripts/detect.py:223-227 are then fused into the kernel's gather)."""
         w, b, k, s, silu = self.fold(m)
-        Bn, Cin, H, W = x_nchw.shape
+        u8 = x.dtype == torch.uint8
+        if u8:
+            Bn, H, W, Cin = x.shape
+        else:
+            Bn, Cin, H, W = x.shape
         Ho, Wo = (H + 2 - 3) // s + 1, (W + 2 - 3) // s + 1
         out = self.alloc(Ho, Wo, w.shape[0], layout=L.PHASE4 if phase4 else L.NHWC)
         wp = self.dev(w.permute(0, 2, 3, 1), torch.float32)
         bp = self.dev(b, torch.float32)
-        d = L.StemDesc(x_nchw.data_ptr(), Bn, Cin, H, W, out.c(), wp.data_ptr(), bp.data_ptr(), s,
-                       L.ACT_SILU if silu else L.ACT_NONE)
+        d = L.StemDesc(None if u8 else x.data_ptr(), Bn, Cin, H, W, out.c(), wp.data_ptr(), bp.data_ptr(), s,
+                       L.ACT_SILU if silu else L.ACT_NONE, x.data_ptr() if u8 else None)
         L.check(self.lib.yre_plan_add_stem(self.h, C.byref(d)), "plan_add_stem")
-        self.trace.append(("stem", dict(x=x_nchw, y=out, w=wp, b=bp, stride=s, silu=silu)))
+        self.trace.append(("stem", dict(x=x, y=out, w=wp, b=bp, stride=s, silu=silu, u8=u8)))
         return out
 
     def copy(self, src: V, dst: V) -> None:
@@ -402,7 +408,7 @@ class Plan:
                            f"{' +res' if a['res'] is not None else ''}{' f32out' if y.dtype == L.F32 else ''}")
             elif kind == "stem":
                 y = a["y"]
-                out.append(f"stem {a['x'].shape[1]}->{y.C} @{y.H}x{y.W} B{y.B}")
+                out.append(f"stem {'u8 ' if a.get('u8') else ''}3->{y.C} @{y.H}x{y.W} B{y.B}")
             elif kind in ("adown", "spp", "upsample"):
                 x = a["x"]
                 out.append(f"{kind} C{x.C} @{x.H}x{x.W} B{x.B}")
@@ -435,17 +441,24 @@ def _out_channels(layer, cin: list[int]) -> int:
 
 
 def _weights_version(model: nn.Module) -> int:
-    v = 0
+    """Fingerprint of the weights a plan was folded from: storage address and in-place version counter of every
+    parameter and buffer.  Catches optimizer steps, ``load_state_dict``, ``p.copy_()``, ``p.data = new`` ...;
+    writes THROUGH ``.data`` (``p.data.copy_()``, ``bias.data[:] = ...``) bump no counter and move no storage --
+    after such an edit call ``model.invalidate()``."""
+    h = 0
     for t in model.parameters():
-        v += t._version
+        h = hash((h, t.data_ptr(), t._version))
     for t in model.buffers():
-        v += t._version
-    return v
+        h = hash((h, t.data_ptr(), t._version))
+    return h
 
 
 def compile_model(model, x: torch.Tensor) -> Plan:
-    """Compiles the whole YOLO graph for x's shape/device."""
-    Bn, Cin, H, W = x.shape
+    """Compiles the whole YOLO graph for x's shape/device (x: fp32 [B,C,H,W] or uint8 [B,H,W,3] BGR frames)."""
+    if x.dtype == torch.uint8:
+        Bn, H, W, Cin = x.shape
+    else:
+        Bn, Cin, H, W = x.shape
     p = Plan(x.device, Bn, model.precision)
     names = list(model.layers.keys())
     conn = model.connections
@@ -547,10 +560,14 @@ def _fresh(p: Plan, t: torch.Tensor) -> torch.Tensor:
 
 def _replay_graph(p: Plan, x: torch.Tensor) -> None:
     """Static-buffer mode: the whole launch list (incl. its programmatic-dependent-launch edges) is captured once per
-    input pointer into a CUDA graph and replayed -- no per-launch CPU work, ~1 us between kernels."""
+    input BUFFER into a CUDA graph and replayed -- no per-launch CPU work, ~1 us between kernels.  Meant for callers
+    that reuse a few input buffers (a double-buffered upload ring): every new buffer address costs a warm-up run and a
+    capture.  At most 8 (graph, buffer) pairs are held; the oldest pair is dropped together, so a caller that passes
+    a fresh tensor every time pays the capture each call but does not accumulate memory."""
     graphs = p.__dict__.setdefault("graphs", {})
     key = x.data_ptr()
-    g = graphs.get(key)
+    ent = graphs.get(key)
+    g = ent[0] if ent is not None else None
     if g is None:
         cur = torch.cuda.current_stream(p.device)
         side = torch.cuda.Stream(p.device)
@@ -562,9 +579,8 @@ def _replay_graph(p: Plan, x: torch.Tensor) -> None:
         with torch.cuda.graph(g):
             p.run()
         if len(graphs) >= 8:
-            graphs.pop(next(iter(graphs)))
-        graphs[key] = g
-        p.keep.append(x)                             # the captured graph reads this buffer
+            graphs.pop(next(iter(graphs)))           # drops the graph AND the input buffer it pinned
+        graphs[key] = (g, x)                         # the captured graph reads this buffer: keep it alive with the graph
     g.replay()
 
 
@@ -572,9 +588,16 @@ def model_forward(model, x: torch.Tensor):
     if not x.is_cuda:
         raise L.YreError("the yolo-re B200 path runs on CUDA tensors only (there is no CPU fallback)")
     if x.dim() != 4:
-        raise ValueError("expected input [B,C,H,W]")
-    x = x.contiguous().float()
-    key = (tuple(x.shape), x.device.index, model.precision, bool(getattr(model, "main_only", False)))
+        raise ValueError("expected input [B,C,H,W] (or uint8 frames [B,H,W,3])")
+    if x.dtype == torch.uint8:
+        # extension of the reference API: cv2-layout frames (uint8 HWC, BGR) already letterboxed to the model size;
+        # scripts/detect.py:223-227 (BGR->RGB, HWC->CHW, /255) is fused into the first conv's gather
+        if x.shape[3] != 3:
+            raise ValueError("uint8 input must be [B,H,W,3] BGR frames")
+        x = x.contiguous()
+    else:
+        x = x.contiguous().float()
+    key = (tuple(x.shape), x.dtype, x.device.index, model.precision, bool(getattr(model, "main_only", False)))
     p = model._plans.get(key)
     if p is not None and model.check_weights and p.weight_version != _weights_version(model):
         p = None

@@ -58,28 +58,45 @@ def letterbox(img, new_shape: int = 640, color: tuple[int, int, int] = (114, 114
     return (out.cpu().numpy() if was_numpy else out), (r, r), pad
 
 
-def preprocess(imgs, new_shape: int = 640, color: tuple[int, int, int] = (114, 114, 114), out: torch.Tensor | None = None):
+def preprocess(imgs, new_shape: int = 640, color: tuple[int, int, int] = (114, 114, 114), out: torch.Tensor | None = None,
+               dtype: torch.dtype = torch.float32):
     """Fused letterbox + BGR->RGB + HWC->CHW + /255 for a list of images (or one image).
 
     Returns (x [B, 3, S, S] fp32 on the device, ratios [(r, r)], pads [(pad_w, pad_h)]) -- x is the tensor the
-    reference builds at scripts/detect.py:223-227, ready for ``model(x)``."""
+    reference builds at scripts/detect.py:223-227, ready for ``model(x)``.
+
+    ``dtype=torch.uint8`` stops after the letterbox and returns the frames as one uint8 [B, S, S, 3] BGR batch;
+    ``model(x_u8)`` then fuses BGR->RGB / HWC->CHW / /255 into its first convolution, so the fp32 image tensor is
+    never written (4x less traffic on both sides of it).  Detections are identical either way."""
     if isinstance(imgs, (np.ndarray, torch.Tensor)) and imgs.ndim == 3:
         imgs = [imgs]
     srcs = [_to_device_u8(i) for i in imgs]
     dev = srcs[0].device
+    if dtype not in (torch.float32, torch.uint8):
+        raise ValueError("preprocess: dtype must be torch.float32 or torch.uint8")
+    shape = (len(srcs), 3, new_shape, new_shape) if dtype == torch.float32 else (len(srcs), new_shape, new_shape, 3)
     if out is None:
-        out = torch.empty((len(srcs), 3, new_shape, new_shape), dtype=torch.float32, device=dev)
-    if tuple(out.shape) != (len(srcs), 3, new_shape, new_shape) or out.dtype != torch.float32 or not out.is_contiguous() or not out.is_cuda:
-        raise ValueError("preprocess: `out` must be a contiguous CUDA fp32 [B, 3, S, S] tensor")
+        out = torch.empty(shape, dtype=dtype, device=dev)
+    if tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError(f"preprocess: `out` must be a contiguous CUDA {dtype} tensor of shape {shape}")
     ratios, pads = [], []
     descs = (L.LetterboxDesc * len(srcs))()
     for i, src in enumerate(srcs):
         d, r, pad = _desc(src, new_shape, color)
-        d.out_mode, d.dst = L.LB_F32_CHW, out[i].data_ptr()
+        d.out_mode, d.dst = (L.LB_F32_CHW if dtype == torch.float32 else L.LB_U8_HWC), out[i].data_ptr()
         descs[i] = d
         ratios.append((r, r)); pads.append(pad)
     L.check(L.lib().yre_letterbox_u8_batch(descs, len(srcs), _stream()), "letterbox_u8_batch")
     return out, ratios, pads
+
+
+def scale_rows(ratios, pads, orig_shapes, device=None) -> torch.Tensor:
+    """fp32 [B, 5] rows (pad_w, pad_h, gain, orig_w, orig_h) for ``nms_raw(..., scale=...)`` /
+    ``non_max_suppression_async(..., scale=...)``: the ``ratio_pad`` form of scale_boxes (scripts/detect.py:100-101)
+    for every image of a batch, so the box rescale/clip runs inside the NMS output pass."""
+    rows = [[float(p[0]), float(p[1]), float(r[0]), float(o[1]), float(o[0])] for r, p, o in zip(ratios, pads, orig_shapes)]
+    t = torch.tensor(rows, dtype=torch.float32)
+    return t.to(device, non_blocking=True) if device is not None else t
 
 
 def scale_boxes(boxes: torch.Tensor, img_shape, orig_shape, ratio_pad=None) -> torch.Tensor:
