@@ -1,29 +1,41 @@
 #!/usr/bin/env python
-"""Headline benchmark: gelan-c 640x640 detection inference, images/sec INCLUDING NMS.
+"""Headline benchmark: detection inference images/sec INCLUDING NMS (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (N > 1, one rank per GPU)
 
-One "step" = one pass of the hot path (forward + DFL decode + batched NMS, conf 0.25 / iou 0.45) over a
-batch of 64 synthetic 640x640 images per GPU (BASELINE.json configs[1]; at N=8 the global batch is the
-512 of configs[2]).  Images shard across ranks with no collective on the data path;
-NCCL only gathers the timing.  Prints ONE JSON line (rank 0).
+One "step" = one pass of the hot path (forward + DFL decode + batched NMS) over one batch of synthetic images per GPU.
+`--config` picks the BASELINE.json configuration (default 2, the one the metric is quoted on):
 
-  value      images/s, device-timed (CUDA events), inputs already resident in HBM
-  e2e        same metric through the public API from pinned HOST memory: H2D of the batch and D2H of
-             the detections inside the timed region, every step
-  roofline   the conv kernels (dominant, tensor-bound): algorithmic FLOPs of the folded graph /
-             their summed device time, measured per launch with CUDA events
+  2  gelan-c 640x640, 64 images per GPU, NMS conf .25 / iou .45            (weak scaling; N=8 is the 512 of configs[2])
+  3  gelan-c 640x640, GLOBAL batch 512 split over the N GPUs               (strong scaling: 256/128/64 per GPU at 2/4/8)
+  4  yolov9-c 640x640 (dual head), 16 images per GPU                       (N=8 is the batch 128 of configs[3]);
+     `--main-only` compiles the main branch only
+  5  gelan-c 1280x1280, 16 images per GPU, conf .001 / iou .6, max_det 300 (NMS / decode stress: every anchor a candidate)
+
+Images shard across ranks with no collective on the data path; NCCL only gathers the timing.
+Prints ONE JSON line (rank 0).
+
+  value      images/s, device-timed (CUDA events), inputs already resident in HBM, through the PUBLIC API:
+             YOLO.forward + non_max_suppression_async(...).result() -- i.e. including the D2H of the per-image counts
+             and the slicing into the reference's list[Tensor[n,6]]; the next batch's forward is enqueued before the
+             host blocks on the previous batch's counts
+  e2e        same metric from pinned HOST memory: uint8 HWC BGR frames (what cv2 delivers) -> H2D -> fused
+             uint8 stem (BGR->RGB, HWC->CHW, /255 in the first conv's gather) -> NMS -> D2H of the detections, every step
+  roofline   the conv kernels (dominant, tensor-bound): SURVEY 8d algorithmic FLOPs of the folded graph / their summed
+             device time (per-launch CUDA events); `frac` is against the BURST cuBLAS bf16 peak of MEASURED_PEAKS.json
+             (kernels timed alone), `frac_sustained` against the sustained one; `stages` holds the HBM-bound kernels
+             (DFL decode, NMS filter) against the measured copy bandwidth
   cpu_baseline  the oracle port of the reference forward+NMS on the box's host cores (bounded sample)
 
-`--impl reference` times the reference algorithm's CPU port (oracle/, the reference itself is pure
-Python/PyTorch and is not present on the GPU box) on the same config/metric.
+`--impl reference` times the reference algorithm's CPU port (oracle/, the reference itself is pure Python/PyTorch and
+is not present on the GPU box) on the same config/metric.
 
-Use of oracle/ here: (1) the cpu_baseline leg and the reference arm execute it (that is what they measure);
-(2) both arms take their SYNTHETIC DATA from it -- `calibrated_state_dict` (the calibrated random-init weight recipe of
-SURVEY.md 8d, which needs one CPU train-mode forward to set the BatchNorm statistics) and the graph description it is
-built from -- so that the two arms run the same weights.  No number of the timed GPU path is computed by oracle/: the
-product (yolo_b200 + libyre.so) never imports it and fails loudly without the CUDA library.
+Use of oracle/ here: (1) the cpu_baseline leg and the reference arm execute it (that is what they measure); (2) both arms
+take their SYNTHETIC WEIGHTS from `oracle.gelan_ref.calibrated_state_dict` (the calibrated random-init recipe of SURVEY.md
+8d needs one CPU train-mode forward to set the BatchNorm statistics) so that the two arms run the same weights.  The
+synthetic images come from bench_data.py.  No number of the timed GPU path is computed by oracle/: the product
+(yolo_b200 + libyre.so) never imports it and fails loudly without the CUDA library.
 """
 from __future__ import annotations
 
@@ -44,19 +56,34 @@ sys.path.insert(0, str(ROOT / "yolo-re_b200"))
 
 import torch  # noqa: E402
 
-CFG = ROOT / "configs" / "models" / "gelan-c.yaml"
-IMG = 640
-PER_GPU_BATCH = 64
-CONF, IOU, MAX_DET = 0.25, 0.45, 300
-GF_PER_IMAGE_FOLDED = 102.136e9      # SURVEY.md section 8d, gelan-c @640 folded graph
+from bench_data import make_inputs  # noqa: E402
+
+MAX_DET = 300
+# gf = algorithmic conv FLOPs per image of the FOLDED graph, SURVEY.md section 8d (the figure roofline.achieved uses)
+CONFIGS = {
+    2: dict(model="gelan-c", img=640, per_gpu=64, global_batch=None, scaling="weak", conf=0.25, iou=0.45, gf=102.136e9,
+            metric="gelan-c 640x640 images/sec incl. NMS",
+            workload="gelan-c inference 640x640 + DFL decode + NMS(conf=0.25, iou=0.45), calibrated random-init weights"),
+    3: dict(model="gelan-c", img=640, per_gpu=None, global_batch=512, scaling="strong", conf=0.25, iou=0.45, gf=102.136e9,
+            metric="gelan-c 640x640 images/sec incl. NMS",
+            workload="gelan-c inference 640x640, global batch 512 sharded over the GPUs + DFL decode + NMS(conf=0.25, iou=0.45)"),
+    4: dict(model="yolov9-c", img=640, per_gpu=16, global_batch=None, scaling="weak", conf=0.25, iou=0.45, gf=237.630e9,
+            metric="yolov9-c 640x640 images/sec incl. NMS",
+            workload="yolov9-c (dual head, aux + main branch) inference 640x640, 16 images per GPU (batch 128 on 8 GPUs) + "
+                     "DFL decode + NMS(conf=0.25, iou=0.45) on the main head"),
+    5: dict(model="gelan-c", img=1280, per_gpu=16, global_batch=None, scaling="weak", conf=0.001, iou=0.6, gf=408.545e9,
+            metric="gelan-c 1280x1280 images/sec incl. NMS (conf 0.001)",
+            workload="gelan-c inference 1280x1280 (33600 anchors), 16 images per GPU + DFL decode + NMS(conf=0.001, iou=0.6, "
+                     "max_det=300): every anchor is a candidate"),
+}
 
 
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
         d = json.loads(p.read_text())
-        return d.get("bf16_tflops_sustained", 1374.1), d.get("hbm_gbs", 6549.8), "measured"
-    return 1400.0, 6650.0, "fallback"
+        return d.get("bf16_tflops", 1644.5), d.get("bf16_tflops_sustained", 1374.1), d.get("hbm_gbs", 6549.8), "measured (MEASURED_PEAKS.json)"
+    return 1400.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -96,50 +123,50 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(batch: int, seed: int = 7) -> torch.Tensor:
-    """Seeded multi-octave images in [0,1] (oracle.gelan_ref.fractal; matches /255 preprocessing).  With the
-    calibrated weights ~1-5 % of the anchors pass conf 0.25, so NMS does real work."""
-    from oracle import gelan_ref as G
-    g = torch.Generator().manual_seed(seed)
-    base = G.fractal(min(batch, 8), IMG, g)
-    reps = -(-batch // base.shape[0])
-    x = base.repeat(reps, 1, 1, 1)[:batch].clone()
-    # de-duplicate the repeats with a per-image brightness ramp (keeps values in [0,1])
-    x *= torch.linspace(0.85, 1.0, batch).view(-1, 1, 1, 1)
-    return x
-
-
-def cpu_reference_step(nodes, nc, sd, x):
+def cpu_reference_step(nodes, nc, sd, x, conf, iou):
     from oracle import gelan_ref as G
     from oracle import nms_ref as N
     y, _ = G.forward(nodes, nc, sd, x)
-    return N.non_max_suppression(y.permute(0, 2, 1).contiguous(), CONF, IOU, MAX_DET)
+    if isinstance(y, (list, tuple)):        # dual head: callers use the main branch (scripts/detect.py:239-241)
+        y = y[1]
+    return N.non_max_suppression(y.permute(0, 2, 1).contiguous(), conf, iou, MAX_DET)
 
 
-def run_reference(args):
+def per_gpu_batch(cfg: dict, world: int, override: int) -> int:
+    if override > 0:
+        return override
+    if cfg["global_batch"]:
+        if cfg["global_batch"] % world:
+            raise SystemExit(f"global batch {cfg['global_batch']} does not split over {world} GPUs")
+        return cfg["global_batch"] // world
+    return cfg["per_gpu"]
+
+
+def run_reference(args, cfg):
     """--impl reference: the reference algorithm's CPU port on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import gelan_ref as G
     torch.set_num_threads(os.cpu_count() or 1)
-    nodes, nc = G.load_graph(CFG)
+    yaml_path = ROOT / "configs" / "models" / f"{cfg['model']}.yaml"
+    nodes, nc = G.load_graph(yaml_path)
     sd = G.calibrated_state_dict(nodes, nc)
-    sample = 4
-    x = make_inputs(sample)
+    sample = 4 if (cfg["img"] <= 640 and cfg["model"] == "gelan-c") else (2 if cfg["img"] <= 640 else 1)
+    x = make_inputs(sample, cfg["img"])
     for _ in range(args.warmup):
-        cpu_reference_step(nodes, nc, sd, x)
+        cpu_reference_step(nodes, nc, sd, x, cfg["conf"], cfg["iou"])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(nodes, nc, sd, x)
+        cpu_reference_step(nodes, nc, sd, x, cfg["conf"], cfg["iou"])
     dt = (time.perf_counter() - t0) / args.steps
     v = sample / dt
     print(json.dumps({
-        "impl": "reference", "metric": "gelan-c 640x640 images/sec incl. NMS", "value": v, "unit": "images/s",
+        "impl": "reference", "metric": cfg["metric"], "value": v, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "gelan-c inference 640x640 + DFL decode + NMS(conf=0.25, iou=0.45), calibrated random-init weights",
-                   "per_gpu_batch": PER_GPU_BATCH, "sample_batch": sample},
+        "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "baseline_config": args.config,
+                   "per_gpu_batch": per_gpu_batch(cfg, max(1, args.gpus), args.batch), "sample_batch": sample},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} images/step x {args.steps} steps, oracle port of the reference forward + NMS (CPU fp32)"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -153,15 +180,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (default 64 = the metric's config)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configuration (default 2)")
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch of the configuration")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--main-only", action="store_true", help="dual-head models: compile the main branch only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary measurements (fp32-input e2e, default-flags run)")
     ap.add_argument("--per-op", default="", help="write a per-launch CSV (kernel, shape, ms, TFLOP/s) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    cfg = CONFIGS[args.config]
 
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, cfg)
         return
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -181,26 +212,47 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from oracle import gelan_ref as G
-    from yolo_b200 import YOLO, nms_raw, non_max_suppression
+    from oracle import gelan_ref as G               # synthetic weights only (see the module docstring)
+    from yolo_b200 import YOLO, nms_raw, non_max_suppression, non_max_suppression_async
+    from yolo_b200 import _lib as L
 
     torch.set_num_threads(max(1, (os.cpu_count() or 8) // max(world, 1)))
-    nodes, nc = G.load_graph(CFG)
+    yaml_path = ROOT / "configs" / "models" / f"{cfg['model']}.yaml"
+    nodes, nc = G.load_graph(yaml_path)
     sd = G.calibrated_state_dict(nodes, nc)          # deterministic: every rank builds identical weights
-    model = YOLO.from_yaml(CFG)
+    model = YOLO.from_yaml(yaml_path)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval().set_precision(args.precision)
+    model.main_only = bool(args.main_only)
     model.check_weights = False
     model.fresh_outputs = False
     model.use_cuda_graph = os.environ.get("YRE_BENCH_GRAPH", "1") != "0"     # static buffers -> the forward replays as one CUDA graph
 
-    Bn = args.batch
-    x_host = make_inputs(Bn, seed=7 + rank).pin_memory()
+    IMG, CONF, IOU = cfg["img"], cfg["conf"], cfg["iou"]
+    Bn = per_gpu_batch(cfg, world, args.batch)
+    x_host = make_inputs(Bn, IMG, seed=7 + rank).pin_memory()
     x_dev = x_host.to(dev)
+    # the same images as the uint8 HWC BGR frames a camera / cv2.imread delivers
+    u8_host = (x_host.permute(0, 2, 3, 1).flip(-1) * 255.0).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
 
-    def step_resident():
-        y, _ = model(x_dev)
-        return nms_raw(y.permute(0, 2, 1), CONF, IOU, MAX_DET)
+    def pred_of(x):
+        y, _ = model(x)
+        if isinstance(y, (list, tuple)):             # dual head: NMS on the main branch (scripts/detect.py:239-241)
+            y = y[1]
+        return y.permute(0, 2, 1)
+
+    def step_resident():                              # no host sync at all (round-1 definition, kept for comparison)
+        return nms_raw(pred_of(x_dev), CONF, IOU, MAX_DET)
+
+    def run_public(steps):
+        """forward + non_max_suppression through the public API incl. counts D2H + list slicing; one batch in flight."""
+        pend, dets = None, None
+        for _ in range(steps):
+            cur = non_max_suppression_async(pred_of(x_dev), CONF, IOU, MAX_DET)
+            if pend is not None:
+                dets = pend.result()
+            pend = cur
+        return pend.result()
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -208,132 +260,127 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    def allmax(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- warm-up (also compiles the plan) ----
-    for _ in range(args.warmup):
+    run_public(args.warmup)
+    for _ in range(2):
         out, counts, keep = step_resident()
     torch.cuda.synchronize(dev)
-    n_cand_frac = None
     plan = next(iter(model._plans.values()))
     launches_per_step = plan.num_launches + 3
 
-    # ---- device-timed throughput, inputs resident ----
+    # ---- device-timed throughput, inputs resident, public API ----
     sampler = ClockSampler(local)
     sync_all()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    dets = run_public(args.steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms_max = allmax(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * Bn * args.steps / (ms_max / 1e3)
+    dets_per_img = sum(len(d) for d in dets) / max(1, len(dets))
+
+    # the same steps with no host synchronisation (nms_raw): what the host-side tail of the public API costs
+    sync_all()
+    e0.record()
     for _ in range(args.steps):
         out, counts, keep = step_resident()
     e1.record()
     torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * Bn * args.steps / (ms_max / 1e3)
-    dets_per_img = float(counts.float().mean().item())
+    value_nosync = world * Bn * args.steps / (allmax(e0.elapsed_time(e1)) / 1e3)
 
-    # ---- end-to-end through the public API from pinned host memory ----
+    # ---- end-to-end from pinned host memory ----
     copy_stream = torch.cuda.Stream(dev)
-    bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     out_host = torch.empty((Bn, MAX_DET, 6), dtype=torch.float32).pin_memory()
-    cnt_host = torch.empty((Bn,), dtype=torch.int32).pin_memory()
 
-    def e2e_run(steps):
+    def e2e_run(steps, src_host, bufs):
         main_s = torch.cuda.current_stream(dev)
         for b in range(2):
             done[b].record(main_s)
         with torch.cuda.stream(copy_stream):                 # prefetch step 0
             copy_stream.wait_event(done[0])
-            bufs[0].copy_(x_host, non_blocking=True)
+            bufs[0].copy_(src_host, non_blocking=True)
             ready[0].record(copy_stream)
+        pend = None
         for i in range(steps):
             cur, nxt = i & 1, (i + 1) & 1
             if i + 1 < steps:
                 with torch.cuda.stream(copy_stream):         # H2D of step i+1 overlaps the compute of step i
                     copy_stream.wait_event(done[nxt])
-                    bufs[nxt].copy_(x_host, non_blocking=True)
+                    bufs[nxt].copy_(src_host, non_blocking=True)
                     ready[nxt].record(copy_stream)
             main_s.wait_event(ready[cur])
-            y, _ = model(bufs[cur])
-            o, c, _k = nms_raw(y.permute(0, 2, 1), CONF, IOU, MAX_DET)
+            p = non_max_suppression_async(pred_of(bufs[cur]), CONF, IOU, MAX_DET)
             done[cur].record(main_s)
-            out_host.copy_(o, non_blocking=True)             # D2H of the step's result
-            cnt_host.copy_(c, non_blocking=True)
+            out_host.copy_(p.out, non_blocking=True)         # D2H of the step's detections (counts travel inside `p`)
+            if pend is not None:
+                pend.result()
+            pend = p
+        pend.result()
         torch.cuda.synchronize(dev)
 
-    e2e_run(2)
-    sync_all()
-    t0 = time.perf_counter()
-    e2e_run(args.steps)
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * Bn * args.steps / float(t.item())
-    h2d = x_host.numel() * 4
-    d2h = out_host.numel() * 4 + cnt_host.numel() * 4
-
-    # ---- extra (informational): the same step fed from uint8 HWC camera frames through K8 (yolo_b200.preprocess) ----
-    # What scripts/detect.py:223-227 does on the host -- BGR->RGB, HWC->CHW, /255 -- happens on the device, so the H2D
-    # is 4x smaller.  Not the headline `e2e` (whose host buffer is the fp32 tensor the reference's forward takes).
-    e2e_u8 = None
-    try:
-        from yolo_b200 import preprocess
-        u8_host = (x_host.permute(0, 2, 3, 1).flip(-1) * 255.0).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
-        u8_bufs = [torch.empty(u8_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
-        x_u8 = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
-
-        def u8_run(steps):
-            main_s = torch.cuda.current_stream(dev)
-            for b in range(2):
-                done[b].record(main_s)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done[0])
-                u8_bufs[0].copy_(u8_host, non_blocking=True)
-                ready[0].record(copy_stream)
-            for i in range(steps):
-                cur, nxt = i & 1, (i + 1) & 1
-                if i + 1 < steps:
-                    with torch.cuda.stream(copy_stream):
-                        copy_stream.wait_event(done[nxt])
-                        u8_bufs[nxt].copy_(u8_host, non_blocking=True)
-                        ready[nxt].record(copy_stream)
-                main_s.wait_event(ready[cur])
-                xin, _, _ = preprocess(list(u8_bufs[cur]), IMG, out=x_u8[cur])
-                y, _ = model(xin)
-                o, c, _k = nms_raw(y.permute(0, 2, 1), CONF, IOU, MAX_DET)
-                done[cur].record(main_s)
-                out_host.copy_(o, non_blocking=True)
-                cnt_host.copy_(c, non_blocking=True)
-            torch.cuda.synchronize(dev)
-
-        u8_run(2)
-        torch.cuda.synchronize(dev)
-        u8_ok = True
-    except Exception as e:      # informational only; the headline numbers above do not depend on it
-        u8_ok, u8_err = False, f"{type(e).__name__}: {e}"[:200]
-    # every rank reaches the collectives below whatever happened above
-    sync_all()
-    t0 = time.perf_counter()
-    if u8_ok:
+    def timed_e2e(src_host, bufs):
+        ok, err = True, ""
         try:
-            u8_run(args.steps)
-        except Exception as e:
-            u8_ok, u8_err = False, f"{type(e).__name__}: {e}"[:200]
-    tu = torch.tensor([time.perf_counter() - t0 if u8_ok else float("inf")], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tu, op=dist.ReduceOp.MAX)
-    if math.isfinite(float(tu.item())):
-        e2e_u8 = {"value": world * Bn * args.steps / float(tu.item()), "unit": "images/s", "h2d_bytes_per_step": int(u8_host.numel()),
-                  "how": "pinned host uint8 HWC BGR frames -> H2D -> yolo_b200.preprocess (K8) -> YOLO.forward -> nms -> D2H"}
-    else:
-        e2e_u8 = {"error": u8_err if not u8_ok else "failed on another rank"}
+            e2e_run(2, src_host, bufs)
+        except Exception as e:                               # every rank must still reach the collectives below
+            ok, err = False, f"{type(e).__name__}: {e}"[:200]
+        sync_all()
+        t0 = time.perf_counter()
+        if ok:
+            try:
+                e2e_run(args.steps, src_host, bufs)
+            except Exception as e:
+                ok, err = False, f"{type(e).__name__}: {e}"[:200]
+        dt = allmax(time.perf_counter() - t0 if ok else float("inf"))
+        return (world * Bn * args.steps / dt if math.isfinite(dt) else None), err
+
+    u8_bufs = [torch.empty(u8_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+    e2e_value, e2e_err = timed_e2e(u8_host, u8_bufs)
+    d2h = out_host.numel() * 4 + Bn * 4
+    e2e = {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(u8_host.numel()), "d2h_bytes_per_step": d2h,
+           "how": "pinned host uint8 HWC BGR frames (cv2 layout) -> H2D (copy stream, double-buffered) -> YOLO.forward on the "
+                  "uint8 batch (BGR->RGB, HWC->CHW, /255 fused into the first conv) -> non_max_suppression_async -> D2H of "
+                  "detections + counts, every step"}
+    if e2e_value is None:
+        e2e["error"] = e2e_err
+    del u8_bufs
+    e2e_f32 = None
+    if not args.quick:
+        f32_bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+        v, err = timed_e2e(x_host, f32_bufs)
+        e2e_f32 = {"value": v, "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": d2h,
+                   "how": "same, but the host buffer is the fp32 NCHW tensor the reference's forward takes (4x the upload)"}
+        if v is None:
+            e2e_f32["error"] = err
+        del f32_bufs
+
+    # ---- default flags (fresh output tensors every call, weight check, no CUDA graph), synchronous public API ----
+    default_flags = None
+    if not args.quick:
+        model.fresh_outputs, model.check_weights, model.use_cuda_graph = True, True, False
+        for _ in range(2):
+            non_max_suppression(pred_of(x_dev), CONF, IOU, MAX_DET)
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            non_max_suppression(pred_of(x_dev), CONF, IOU, MAX_DET)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        default_flags = world * Bn * args.steps / (allmax(e0.elapsed_time(e1)) / 1e3)
+        model.fresh_outputs, model.check_weights = False, False
+        model.use_cuda_graph = os.environ.get("YRE_BENCH_GRAPH", "1") != "0"
 
     if rank != 0:
         if dist is not None:
@@ -341,9 +388,8 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- NMS device time (3 launches: init, filter, select) ----
-    y_static, _ = model(x_dev)
-    pred_static = y_static.permute(0, 2, 1)
+    # ---- NMS device time: whole (3 launches) and the HBM-bound candidate pass alone ----
+    pred_static = pred_of(x_dev).contiguous()
     torch.cuda.synchronize(dev)
     n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0.record()
@@ -352,6 +398,21 @@ def main():
     n1.record()
     torch.cuda.synchronize(dev)
     nms_ms = n0.elapsed_time(n1) / 5
+    import ctypes as C
+    lib = L.lib()
+    A_total = pred_static.shape[1]
+    ws = torch.empty((lib.yre_nms_workspace_bytes(Bn, A_total),), dtype=torch.uint8, device=dev)
+    fd = L.NmsDesc(pred_static.data_ptr(), Bn, A_total, nc, float(CONF), float(IOU), MAX_DET, None, -1, 0, None, None, None,
+                   ws.data_ptr(), ws.numel(), None)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    L.check(lib.yre_nms_filter_only(C.byref(fd), stream), "nms_filter_only")
+    torch.cuda.synchronize(dev)
+    n0.record()
+    for _ in range(5):
+        lib.yre_nms_filter_only(C.byref(fd), stream)
+    n1.record()
+    torch.cuda.synchronize(dev)
+    filt_ms = n0.elapsed_time(n1) / 5
 
     # ---- per-op device timing: roofline of the conv kernels (rank 0) ----
     table = plan.op_table()
@@ -389,72 +450,94 @@ def main():
             f.write("op,kernel,shape,ms,gflop,tflops,ms_raw\n")
             for i, ((name, fl), tms, desc) in enumerate(zip(table, per_op, plan.op_descriptions())):
                 f.write(f"{i},{name},{desc},{tms:.5f},{fl / 1e9:.3f},{(fl / (tms / 1e3) / 1e12) if tms > 0 else 0:.1f},{per_op_raw[i]:.5f}\n")
-    peak_tf, peak_gbs, peak_src = peaks()
+    peak_burst, peak_sust, peak_gbs, peak_src = peaks()
     fam = {}
     for (name, fl), tms in zip(table, per_op):
         f = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "launches": 0})
         f["ms"] += tms; f["flops"] += fl; f["launches"] += 1
     conv_name = "conv_tc" if "conv_tc" in fam else "conv_ffma"
     cf = fam[conv_name]
-    achieved = cf["flops"] / (cf["ms"] / 1e3) / 1e12 if cf["ms"] > 0 else 0.0
-    all_conv_flops = sum(f["flops"] for n, f in fam.items() if n.startswith("conv") or n == "stem")
+    executed_flops = sum(f["flops"] for n, f in fam.items() if n.startswith("conv"))
+    # algorithmic conv FLOPs of one step (folded graph).  The stem's 0.71 GF/image are part of that
+    # figure but run in the (HBM-bound) stem kernel, so they are taken out of the numerator the conv launches are credited with.
+    stem_flops = fam.get("stem", {"flops": 0.0})["flops"]
+    if args.main_only and cfg["model"] != "gelan-c":
+        algo_flops = executed_flops                  # pruned graph: SURVEY quotes no figure, use the executed (true grouped) FLOPs
+        algo_src = "executed FLOPs of the pruned (main-only) plan"
+    else:
+        algo_flops = cfg["gf"] * Bn - stem_flops
+        algo_src = f"SURVEY 8d: {cfg['gf'] / 1e9:.3f} GF/image folded graph x {Bn} images - stem ({stem_flops / Bn / 1e9:.3f} GF/image, HBM-bound kernel)"
+    achieved = algo_flops / (cf["ms"] / 1e3) / 1e12 if cf["ms"] > 0 else 0.0
     # DRAM bytes of the conv launches of one step, from the committed ncu launch list of this same command
-    # (profiles/*_ncu_launch_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum per kernel family)
     traffic, traffic_src = None, None
     try:
         import csv
         summ = sorted((ROOT / "profiles").glob("r*_ncu_launch_summary.csv"))
-        if summ and Bn == PER_GPU_BATCH:
+        if summ and args.config == 2 and Bn == cfg["per_gpu"]:
             rows = [r for r in csv.DictReader(open(summ[-1])) if r["kernel"].startswith("conv")]
             traffic = sum(float(r["dram_read_MB"]) + float(r["dram_write_MB"]) for r in rows) * 1e6
             traffic_src = f"{summ[-1].name}: {sum(int(r['launches_per_step']) for r in rows)} conv launches of one step"
     except Exception:
         traffic, traffic_src = None, None
-    roofline = {"bound": "tensor", "kernel": conv_name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
-                "traffic_unit": "bytes per step (all conv launches; algorithmic unfused bf16 bytes = 2(|in|+|out|+|w|) = 28.9e9)",
+    # HBM-bound stages against the measured copy bandwidth (algorithmic bytes, DESIGN.md section 3)
+    dec_bytes = Bn * A_total * (144 * 4 + (4 + nc) * 4)           # fp32 raw logits in, fp32 y out
+    filt_bytes = Bn * A_total * (4 + nc) * 4
+    dec_ms = fam["dfl_decode_score"]["ms"] / max(1, fam["dfl_decode_score"]["launches"])
+    stages = {
+        "dfl_decode_score": {"bound": "hbm", "bytes": dec_bytes, "ms": dec_ms, "GBps": dec_bytes / (dec_ms / 1e3) / 1e9,
+                             "frac": dec_bytes / (dec_ms / 1e3) / 1e9 / peak_gbs},
+        "nms_filter": {"bound": "hbm", "bytes": filt_bytes, "ms": filt_ms, "GBps": filt_bytes / (filt_ms / 1e3) / 1e9,
+                       "frac": filt_bytes / (filt_ms / 1e3) / 1e9 / peak_gbs,
+                       "note": "counter reset + candidate pass (yre_nms_filter_only), 2 launches"},
+        "nms_select": {"bound": "alu", "ms": max(0.0, nms_ms - filt_ms), "note": "sort + IoU + greedy scan; reported separately (SURVEY 8d)"},
+    }
+    roofline = {"bound": "tensor", "kernel": conv_name, "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
+                "frac": achieved / peak_burst, "frac_sustained": achieved / peak_sust, "peak_sustained": peak_sust,
+                "peak_source": f"{peak_src}: bf16_tflops (burst) for kernels timed one by one; bf16_tflops_sustained beside it",
+                "traffic": traffic,
+                "traffic_unit": "bytes per step (all conv launches; algorithmic unfused bf16 bytes = 2(|in|+|out|+|w|) = 28.9e9 at config 2)",
                 "traffic_source": traffic_src,
-                "launches_per_step": cf["launches"], "ms_per_step": cf["ms"], "flops_per_step": cf["flops"],
+                "launches_per_step": cf["launches"], "ms_per_step": cf["ms"], "flops_per_step": algo_flops, "flops_source": algo_src,
+                "executed_flops_per_step": executed_flops,
                 "timing": f"per-launch CUDA-event intervals minus the measured event-record gap ({gap_ms * 1e3:.1f} us/interval); "
                           f"all ops: raw {raw_sum:.3f} ms, un-instrumented pass {plain_ms:.3f} ms",
-                "flops_per_image_folded_graph": all_conv_flops / Bn}
+                "stages": stages,
+                "step_share": {"conv_ms": cf["ms"], "plan_ms": plain_ms, "nms_ms": nms_ms,
+                               "nms_share_of_step": nms_ms / (plain_ms + nms_ms)}}
     stage_ms = {n: round(f["ms"], 4) for n, f in fam.items()}
     stage_ms["nms"] = round(nms_ms, 4)
-    # HBM-bound stages against the measured copy bandwidth (algorithmic bytes, DESIGN.md section 3)
-    A = sum((IMG // s_) ** 2 for s_ in (8, 16, 32))
-    dec_bytes = Bn * A * (144 * 4 + 84 * 4)
-    hbm = {"dfl_decode_score": {"bytes": dec_bytes, "GBps": dec_bytes / (fam["dfl_decode_score"]["ms"] / 1e3) / 1e9,
-                                "frac_of_measured_hbm": dec_bytes / (fam["dfl_decode_score"]["ms"] / 1e3) / 1e9 / peak_gbs}}
 
     # ---- CPU baseline: oracle port on the host cores, bounded sample ----
     cpu = None
     if not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)                  # the CPU arm gets every host core again
         torch.set_num_threads(os.cpu_count() or 1)
-        xs = x_host[:2].clone()
-        cpu_reference_step(nodes, nc, sd, xs)
+        ns = 2 if IMG <= 640 else 1
+        xs = x_host[:ns].clone()
+        cpu_reference_step(nodes, nc, sd, xs, CONF, IOU)
         t0 = time.perf_counter()
-        n_runs = 3
+        n_runs = 3 if cfg["model"] == "gelan-c" and IMG <= 640 else 2
         for _ in range(n_runs):
-            ref_dets = cpu_reference_step(nodes, nc, sd, xs)
+            cpu_reference_step(nodes, nc, sd, xs, CONF, IOU)
         cdt = (time.perf_counter() - t0) / n_runs
-        cpu = {"value": 2 / cdt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"2 images x {n_runs} runs of the oracle port (reference forward + NMS, CPU fp32)"}
+        cpu = {"value": ns / cdt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{ns} images x {n_runs} runs of the oracle port (reference forward + NMS, CPU fp32)"}
 
     print(json.dumps({
-        "metric": "gelan-c 640x640 images/sec incl. NMS", "value": value, "unit": "images/s", "n_gpus": world,
+        "metric": cfg["metric"], "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "gelan-c inference 640x640 + DFL decode + NMS(conf=0.25, iou=0.45), calibrated random-init weights",
-                   "per_gpu_batch": Bn, "global_batch": Bn * world, "l2": "input batch (315 MB) and activations exceed the 126 MB L2",
-                   "detections_per_image": dets_per_img, "parallelism": f"image-sharded x{world}, no data-path collective"},
-        "e2e_u8_input": e2e_u8,
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": cfg["workload"], "baseline_config": args.config, "main_only": bool(args.main_only),
+                   "per_gpu_batch": Bn, "global_batch": Bn * world,
+                   "l2": f"input batch ({x_host.numel() * 4 / 1e6:.0f} MB fp32) and activations exceed the 126 MB L2",
+                   "detections_per_image": dets_per_img, "parallelism": f"image-sharded x{world}, no data-path collective",
+                   "value_definition": "YOLO.forward + non_max_suppression_async().result() (counts D2H + list slicing), one batch in flight",
+                   "value_no_host_sync": value_nosync, "value_default_flags": default_flags},
+        "e2e": e2e, "e2e_fp32_input": e2e_f32,
         "host_cores_bound": (len(numa_cpus) if numa_cpus else None),
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "how": "pinned host fp32 batch -> H2D (copy stream, double-buffered) -> YOLO.forward -> nms -> D2H detections"},
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
         "tcgen05_convs_per_step": plan.num_tcgen05,
-        "roofline": roofline, "stage_ms_per_step": stage_ms, "hbm_stages": hbm, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "stage_ms_per_step": stage_ms, "cpu_baseline": cpu, "clocks": clocks,
     }))
     if dist is not None:
         dist.barrier()

@@ -67,6 +67,29 @@ def net_case(cfg: str, size: int, batch: int, seed: int, stride_a: int):
     print(cfg, size, "floor", d["floor_box"], d["floor_score"], "cand", d["n_cand"], "dets", [len(t) for t in dets])
 
 
+def det_case(cfg: str, size: int, batch: int, seed: int):
+    """Final detections (forward + non_max_suppression, conf .25 / iou .45) of the REFERENCE in fp32 on a batch of
+    calibrated-weight images: the yardstick of the bf16 detection-level gate (tests/test_gpu_round2.py)."""
+    nodes, nc = G.load_graph(ROOT / "configs/models" / f"{cfg}.yaml")
+    sd = G.calibrated_state_dict(nodes, nc)
+    m = YOLO.from_yaml(f"/root/reference/configs/models/{cfg}.yaml")
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = G.fractal(batch, size, torch.Generator().manual_seed(seed))
+    with torch.no_grad():
+        y, _ = m(x)
+    if isinstance(y, list):
+        y = y[1]
+    pred = y.permute(0, 2, 1).contiguous()
+    dets = non_max_suppression(pred, 0.25, 0.45)
+    d = {"cfg": cfg, "size": size, "batch": batch, "seed": seed,
+         "n_cand": np.array([(pred[i, :, 4:].max(1).values > 0.25).sum().item() for i in range(batch)])}
+    for i, t in enumerate(dets):
+        d[f"det{i}"] = t.numpy()
+    np.savez_compressed(OUT / f"{cfg}_{size}_dets.npz", **d)
+    print(cfg, size, "dets", [len(t) for t in dets], "cand", d["n_cand"])
+
+
 def nms_cases():
     d = {}
     for name, c in NMS_CASES.items():
@@ -79,7 +102,13 @@ def nms_cases():
 
 
 if __name__ == "__main__":
-    nms_cases()
-    net_case("gelan-c", 128, 2, 11, 1)
-    net_case("gelan-c", 640, 1, 12, 8)
-    net_case("yolov9-c", 64, 1, 13, 1)
+    only = sys.argv[1:]
+    if not only or "nms" in only:
+        nms_cases()
+    if not only or "nets" in only:
+        net_case("gelan-c", 128, 2, 11, 1)
+        net_case("gelan-c", 640, 1, 12, 8)
+        net_case("yolov9-c", 64, 1, 13, 1)
+    if not only or "round2" in only:
+        net_case("yolov9-c", 640, 1, 14, 8)
+        det_case("gelan-c", 640, 8, 31)

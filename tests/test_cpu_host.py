@@ -251,3 +251,43 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(got[name]) == C.sizeof(ct), name
         for f in fields or []:
             assert int(got[f"{name}.{f}"]) == getattr(ct, f).offset, f"{name}.{f}"
+
+
+@pytest.mark.parametrize("nc", [1, 3, 5])
+def test_any_class_count_plan_wiring(dry, nc):
+    """YOLO.from_yaml(num_classes=...) accepts any class count (reference parser.py); the plan pads the class logits to a
+    multiple of 16 channels (zero weights) and the outputs expose exactly nc of them."""
+    nodes, _ = G.load_graph(ROOT / "configs/models/gelan-c.yaml", num_classes=nc)
+    sd = G.default_state_dict(nodes, nc, seed=nc)
+    m = YOLO.from_yaml(ROOT / "configs/models/gelan-c.yaml", num_classes=nc)
+    m.load_state_dict(sd, strict=True)
+    m.eval().set_precision("fp32")
+    x = torch.rand((1, 3, 64, 64), generator=torch.Generator().manual_seed(nc))
+    y_ref, raws_ref = G.forward(nodes, nc, sd, x)
+    p = engine.compile_model(m, x)
+    X.run(p)
+    _, y, raws = p.result
+    yy = y.permute(0, 2, 1)
+    assert yy.shape == y_ref.shape == (1, 4 + nc, 84)
+    assert (yy[:, :4] - y_ref[:, :4]).abs().max() < 2e-2 and (yy[:, 4:] - y_ref[:, 4:]).abs().max() < 2e-4
+    for r, q in zip(raws, raws_ref):
+        got = engine._raw_nchw(r)
+        assert got.shape == q.shape and (got - q).abs().max() < 2e-3
+
+
+def test_uint8_to_unit_interval_is_exact_in_bf16():
+    """k_stem.cu (uint8 stem) builds bf16(float(v) * (1/255)); the fp32-tensor path sees bf16(float(v) / 255)
+    (scripts/detect.py:226).  The two agree for every byte value, so the two stems are bit-identical in bf16 mode."""
+    v = torch.arange(256, dtype=torch.float32)
+    a = (v / 255.0).bfloat16()
+    b = (v * torch.tensor(1.0 / 255.0, dtype=torch.float32)).bfloat16()
+    assert torch.equal(a, b)
+
+
+def test_bench_inputs_match_the_oracle_recipe():
+    import sys
+    sys.path.insert(0, str(ROOT))
+    from bench_data import octave_images
+    a = octave_images(2, 96, torch.Generator().manual_seed(3))
+    b = G.fractal(2, 96, torch.Generator().manual_seed(3))
+    assert torch.equal(a, b)

@@ -37,8 +37,9 @@ template <typename T, int NC>
 __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(16) float sm[];
     const int nc = NC > 0 ? NC : p.nc;
-    const int CH = 64 + nc;                 // floats per raw row
-    const int PITCH = CH + 4;               // keeps 16B alignment, skews banks
+    const int CH = 64 + nc;                 // logits per raw row
+    const int chunks = (CH + 3) / 4;        // 16-byte chunks per row (the last one may run into row padding when nc % 4 != 0)
+    const int PITCH = chunks * 4 + 4;       // keeps 16B alignment, skews banks
     const int OC = 4 + nc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* s_raw = sm + warp * (TILE * PITCH + TILE * OC);   // [TILE][PITCH]
@@ -63,7 +64,6 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
         my_src = dview_pix(p.raw[l], b, py, px); my_lvl = l;
         my_ax = (float)px + 0.5f; my_ay = (float)py + 0.5f; my_st = p.stride[l];
     }
-    const int chunks = CH / 4;
     const int total = na * chunks;
     // Fast path: the tile's anchors are consecutive pixels of ONE level whose view spans the whole buffer,
     // so their raw rows form one contiguous run of na*CH floats.  All loads of a lane are issued into
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
     const int lvl0 = __shfl_sync(0xffffffffu, my_lvl, 0), lvl1 = __shfl_sync(0xffffffffu, my_lvl, na - 1);
     const long long src0 = __shfl_sync(0xffffffffu, my_src, 0);
     constexpr int MAXQ = 10;                                  // one pass for nc <= 96 (9 loads per lane at nc = 80)
-    if (lvl0 == lvl1 && p.raw[lvl0].C_total == CH) {
+    if (lvl0 == lvl1 && p.raw[lvl0].C_total == chunks * 4) {
         const void* basep = p.raw[lvl0].ptr;
         for (int base0 = 0; base0 < total; base0 += 32 * MAXQ) {
             float4 buf[MAXQ];
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
         }
     }
     // ---- class scores: float4 vectors, flat over (anchor, class/4) ----
-    {
+    if ((nc & 3) == 0) {
         const int nc4 = nc / 4;
         for (int i = lane; i < na * nc4; i += 32) {
             const int al = i / nc4, c4 = i - al * nc4;
@@ -149,6 +149,11 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
             float4 r;
             r.x = sigmoid_fast(z.x); r.y = sigmoid_fast(z.y); r.z = sigmoid_fast(z.z); r.w = sigmoid_fast(z.w);
             *reinterpret_cast<float4*>(s_out + al * OC + 4 + c4 * 4) = r;
+        }
+    } else {                                // any class count (YOLO.from_yaml(num_classes=...)): scalar, rows are not 16-byte multiples
+        for (int i = lane; i < na * nc; i += 32) {
+            const int al = i / nc, c = i - al * nc;
+            s_out[al * OC + 4 + c] = sigmoid_fast(s_raw[al * PITCH + 64 + c]);
         }
     }
     __syncwarp();
@@ -169,15 +174,18 @@ __global__ void __launch_bounds__(WARPS * 32) decode_kernel(const DecodeParams p
 int launch_decode(const yre_decode_desc& d, cudaStream_t s) {
     if (d.levels < 1 || d.levels > MAXL) YRE_FAIL(YRE_EINVAL, "decode: levels=%d", d.levels);
     if (!d.y) YRE_FAIL(YRE_EINVAL, "decode: null pointer");
-    if (d.nc < 1 || d.nc % 4) YRE_FAIL(YRE_EUNSUPPORTED, "decode: nc=%d must be a positive multiple of 4", d.nc);
+    if (d.nc < 1) YRE_FAIL(YRE_EINVAL, "decode: nc=%d", d.nc);
     DecodeParams p;
     p.levels = d.levels; p.nc = d.nc; p.y = d.y;
     int A = 0;
     for (int l = 0; l < d.levels; ++l) {
         const yre_view& v = d.raw[l];
         if (yre_check_view(&v, "decode.raw")) return YRE_EINVAL;
-        if (v.layout != YRE_NHWC || v.C != 64 + d.nc || v.c_off % 4 || v.C_total % 4 || v.dtype != d.raw[0].dtype || v.B != d.raw[0].B)
-            YRE_FAIL(YRE_EINVAL, "decode: level %d must be an NHWC [B,H,W,%d] view", l, 64 + d.nc);
+        // rows are read as 16-byte chunks: the pixel pitch must be a multiple of 4 and, when nc % 4 != 0, leave room for the
+        // last partial chunk (the host pads the raw buffer's channel count, engine.towers)
+        if (v.layout != YRE_NHWC || v.C != 64 + d.nc || v.c_off % 4 || v.C_total % 4 || v.c_off + (64 + d.nc + 3) / 4 * 4 > v.C_total ||
+            v.dtype != d.raw[0].dtype || v.B != d.raw[0].B)
+            YRE_FAIL(YRE_EINVAL, "decode: level %d must be an NHWC [B,H,W,%d] view with a pixel pitch that is a multiple of 4", l, 64 + d.nc);
         p.raw[l] = make_dview(v);
         p.stride[l] = d.stride[l];
         p.a_start[l] = A;
@@ -186,8 +194,8 @@ int launch_decode(const yre_decode_desc& d, cudaStream_t s) {
     p.a_start[d.levels] = A;
     p.A = A; p.B = d.raw[0].B;
     for (int k = 0; k < 16; ++k) p.dfl_w[k] = d.dfl_w[k];
-    const int CH = 64 + d.nc, OC = 4 + d.nc;
-    const size_t smem = (size_t)WARPS * (TILE * (CH + 4) + TILE * OC) * sizeof(float);
+    const int CH4 = (64 + d.nc + 3) / 4 * 4, OC = 4 + d.nc;
+    const size_t smem = (size_t)WARPS * (TILE * (CH4 + 4) + TILE * OC) * sizeof(float);
     const long long tiles = (long long)((A + TILE - 1) / TILE) * p.B;
     dim3 grid((unsigned)((tiles + WARPS - 1) / WARPS));
     if (smem > 200 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "decode: nc=%d too large for the staging tile", d.nc);

@@ -133,7 +133,9 @@ class Plan:
         return d
 
     def fold(self, m) -> tuple[torch.Tensor, torch.Tensor, int, int, bool]:
-        """(w[Cout,Cin,k,k] fp64 dense, b[Cout] fp64, k, stride, silu) of a blocks.Conv / RepConv / nn.Conv2d."""
+        """(w[Cout,Cin,k,k] fp64 dense, b[Cout] fp64, k, stride, silu) of a blocks.Conv / RepConv / nn.Conv2d.
+        The folding arithmetic runs on the HOST in fp64 (the parameters are copied down once per compile): no torch
+        element-wise kernels are launched on the device, only the folded weights are uploaded."""
         if isinstance(m, B.RepConv):
             w3, b3, _, s, _ = self.fold(m.conv1)
             w1, b1, _, _, _ = self.fold(m.conv2)
@@ -145,17 +147,17 @@ class Plan:
             k = cv.kernel_size[0]
             if cv.kernel_size[0] != cv.kernel_size[1] or cv.padding[0] != k // 2 or cv.dilation[0] != 1:
                 raise L.YreError(f"unsupported conv geometry {cv}")
-            w = cv.weight.detach().double()
-            scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+            w = cv.weight.detach().cpu().double()
+            scale = bn.weight.detach().cpu().double() / torch.sqrt(bn.running_var.detach().cpu().double() + bn.eps)
             w = self._dense(w * scale[:, None, None, None], cv.groups)
-            b = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+            b = bn.bias.detach().cpu().double() - bn.running_mean.detach().cpu().double() * scale
             if not isinstance(m.act, (nn.SiLU, nn.Identity)):
                 raise L.YreError(f"unsupported activation {m.act}")
             return w, b, k, cv.stride[0], isinstance(m.act, nn.SiLU)
         if isinstance(m, nn.Conv2d):
             k = m.kernel_size[0]
-            w = self._dense(m.weight.detach().double(), m.groups)
-            b = m.bias.detach().double() if m.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64, device=w.device)
+            w = self._dense(m.weight.detach().cpu().double(), m.groups)
+            b = m.bias.detach().cpu().double() if m.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64, device=w.device)
             return w, b, k, m.stride[0], False
         raise L.YreError(f"cannot fold {type(m).__name__}")
 
@@ -299,7 +301,11 @@ class Plan:
         for i, f in enumerate(feats):
             c2 = box[i][0].conv.out_channels
             c3 = cls[i][0].conv.out_channels
-            raw = self.alloc(f.H, f.W, 4 * REG_MAX + nc, dtype=L.F32)
+            # class count padded to a multiple of 16 (zero weights, zero bias): any num_classes keeps 16-byte rows for the
+            # decode kernel and a tcgen05-eligible Cout; the padding channels are never read or returned
+            ncp = -(-nc // 16) * 16
+            raw_full = self.alloc(f.H, f.W, 4 * REG_MAX + ncp, dtype=L.F32)
+            raw = raw_full.sl(0, 4 * REG_MAX + nc)
             if f.H % 16 == 0 and f.W % 8 == 0 and f.H * f.W >= 4096 and c3 % 128 == 0:
                 # large level: the 128-wide N tiles of the cls conv take the paired halo kernel (two patches per
                 # weight box); a merged 64+256 = 320-channel GEMM would fall back to 160-wide unpaired tiles
@@ -310,7 +316,11 @@ class Plan:
             hb = self.conv_m(box[i][1], hb_in)
             self.conv_m(box[i][2], hb, out=raw.sl(0, 4 * REG_MAX))
             hc = self.conv_m(cls[i][1], hc_in)
-            self.conv_m(cls[i][2], hc, out=raw.sl(4 * REG_MAX, nc))
+            wc, bc, kc, sc, silu_c = self.fold(cls[i][2])
+            if ncp != nc:
+                wc = torch.cat([wc, wc.new_zeros((ncp - nc,) + tuple(wc.shape[1:]))])
+                bc = torch.cat([bc, bc.new_zeros(ncp - nc)])
+            self.conv(hc, wc, bc, kc, sc, silu_c, out=raw_full.sl(4 * REG_MAX, ncp))
             raws.append(raw)
         A = sum(r.H * r.W for r in raws)
         y = torch.empty((self.batch, A, 4 + nc), dtype=torch.float32, device=self.device)
@@ -627,8 +637,14 @@ def model_forward(model, x: torch.Tensor):
             p.run()
     p.x_keepalive = x
     if kind == "single":
-        return y.permute(0, 2, 1), [r.t.permute(0, 3, 1, 2) for r in raws]
-    return [t.permute(0, 2, 1) for t in y], [[r.t.permute(0, 3, 1, 2) for r in rs] for rs in raws]
+        return y.permute(0, 2, 1), [_raw_nchw(r) for r in raws]
+    return [t.permute(0, 2, 1) for t in y], [[_raw_nchw(r) for r in rs] for rs in raws]
+
+
+def _raw_nchw(r: "V") -> torch.Tensor:
+    """[B,64+nc,H,W] view of a raw-logit buffer (its channel count may be padded, towers())."""
+    t = r.t if r.C == r.C_total else r.t[..., r.c_off:r.c_off + r.C]
+    return t.permute(0, 3, 1, 2)
 
 
 # ---- standalone block call (tests, teacher-forced stage checks) ----------------------------------------------
@@ -675,8 +691,8 @@ def compile_module(m: nn.Module, x, prec: str | None = None):
     if isinstance(out, tuple) and out and out[0] in ("single", "dual"):
         kind, y, raws = out
         if kind == "single":
-            return p, (y.permute(0, 2, 1), [r.t.permute(0, 3, 1, 2) for r in raws])
-        return p, ([t.permute(0, 2, 1) for t in y], [[r.t.permute(0, 3, 1, 2) for r in rs] for rs in raws])
+            return p, (y.permute(0, 2, 1), [_raw_nchw(r) for r in raws])
+        return p, ([t.permute(0, 2, 1) for t in y], [[_raw_nchw(r) for r in rs] for rs in raws])
     return p, back(out)
 
 
