@@ -63,8 +63,7 @@ def test_num_classes_override_and_groups():
     det = m.layers["detect"]
     assert isinstance(det, DetectDFL) and det.num_outputs == 20 + 64
     assert det.cls_convs[0][2].out_channels == 20
-    g = m.optim_groups(5e-4)
-    assert len(g) == 3 and g[0]["weight_decay"] == 5e-4 and g[1]["weight_decay"] == 0.0
+    assert not hasattr(m, "optim_groups")        # training API (model.py:165-203) is out of scope: not mirrored
 
 
 def test_no_cpu_fallback_and_no_train_forward():

@@ -1157,9 +1157,21 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     p.mtiles = (int)mtiles;
     p.upn = (int)((mtiles + p.npair - 1) / p.npair);
     p.num_units = p.upn * p.tiles_n;
-    // CTA pairs for the wide N tiles of the generic kernel (its shared-memory port bound: 4 KB + 32 N bytes read and as
-    // many written per 128 x N x 16 MMA; a pair halves the weight half of both)
-    p.cta2 = (!p.halo && bn >= 128 && mtiles >= 2 && env_int("YRE_TC_CTA2", 1) != 0) ? 1 : 0;
+    // CTA pairs for the wide N tiles of the generic kernel.  What they buy is operand traffic: per 128 x N x 64 k-iteration a
+    // CTA pulls 16 KB of A + N * 128 B of B from L2 (and the MMAs read as much from shared memory); a pair halves the B half.
+    // Measured at batch 64 (profiles/r02_notes.md): layers whose main loop dominates (K >= 576, or K = 512 with two N tiles)
+    // gain 7-15 % (1x1 1024->512 @40x40: 110 -> 95 us), short-K tiles are epilogue-bound and LOSE 10-40 % to the cross-CTA
+    // accumulator hand-off, and launches with fewer than four rounds of units lose to the cluster start-up unless K is huge.
+    {
+        const long long K_total = (long long)p.taps * Cin;
+        const long long units2 = ((mtiles + 1) / 2) * p.tiles_n;
+        int want = (!p.halo && bn >= 128 && mtiles >= 2 && (K_total >= 576 || (K_total >= 512 && p.tiles_n >= 2)) &&
+                    (units2 >= 2 * sms || K_total >= 4096)) ? 1 : 0;
+        const int f = env_int("YRE_TC_CTA2", -1);          // tuning builds: 0 = never, 1 = whenever legal
+        if (f == 0) want = 0;
+        if (f == 1) want = (!p.halo && bn >= 128 && mtiles >= 2) ? 1 : 0;
+        p.cta2 = want;
+    }
     if (p.cta2) p.num_units = (int)((mtiles + 1) / 2) * p.tiles_n;
     p.a_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
     if (p.halo) {

@@ -8,12 +8,15 @@
 //   nms_filter  HBM-bound pass over pred[B][A][4+nc]: per-anchor first-max class, strict
 //               `conf > thr` (+ optional class filter), xywh->xyxy, per-image max coordinate,
 //               compaction of (score, anchor) sort keys
-//   nms_select  one CTA per image: bitonic sort of the 64-bit keys (== stable descending score
-//               sort, ties -> lower anchor first), then a chunked greedy scan: every chunk of
-//               CHUNK sorted candidates is tested against the boxes kept so far (<= max_det of
-//               them), an IoU bitmask is built inside the chunk, and a serial pass over the
-//               bitmask resolves it.  The scan stops as soon as max_det boxes are kept, which
-//               is exactly `keep[:max_det]` of the reference -- there is no pre-NMS top-k cap.
+//   nms_select  one CTA (1024 threads) per image: bitonic sort of the 64-bit keys (== stable descending
+//               score sort, ties -> lower anchor first) -- in shared memory; above 8192 candidates the
+//               network is run segment-wise (8192-key segments sorted / merged in shared memory, only the
+//               few stages with a compare distance >= 8192 touch global memory) -- then a chunked greedy
+//               scan: every chunk of CHUNK sorted candidates is tested against the boxes kept so far
+//               (<= max_det of them, two threads per candidate), an IoU bitmask is built inside the chunk
+//               (32 warps), and one thread resolves the chunk by walking the set bits of the survivors.
+//               The scan stops as soon as max_det boxes are kept, which is exactly `keep[:max_det]` of the
+//               reference -- there is no pre-NMS top-k cap.
 //
 // Bit-exactness notes: every fp32 op is an explicitly rounded intrinsic (no FMA contraction);
 // the class offset is `float(cls) * (max_coord + 1)` then `box + offset` as two rounded ops
@@ -23,9 +26,10 @@
 
 namespace {
 
-constexpr int CHUNK = 512;            // == threads of nms_select
+constexpr int CHUNK = 512;            // candidates per greedy round
+constexpr int NT_SEL = 1024;          // threads of nms_select (two per candidate of a chunk)
 constexpr int CW = CHUNK / 64;        // mask words per row
-constexpr int SMEM_KEYS = 8192;       // keys sorted in shared memory when they fit
+constexpr int SMEM_KEYS = 8192;       // keys sorted in shared memory at a time (one segment)
 
 typedef unsigned long long u64;
 
@@ -172,22 +176,82 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const flo
     return (double)iou > thr;
 }
 
-__device__ void bitonic_sort(u64* d, int np) {
-    for (int k = 2; k <= np; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < (np >> 1); i += blockDim.x) {
-                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const int hi = lo | j;
-                const bool asc = (lo & k) == 0;
-                const u64 a = d[lo], b = d[hi];
-                if ((a > b) == asc) { d[lo] = b; d[hi] = a; }
-            }
-            __syncthreads();
+// bitonic network stages of merge size k with compare distances j = j_hi, j_hi/2, ..., 1 on the np_local keys in d
+// (shared memory); `base` = global index of d[0] (the sort direction of an element depends on its GLOBAL index)
+__device__ __forceinline__ void bitonic_local(u64* d, int np_local, int base, int k, int j_hi) {
+    for (int j = j_hi; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < (np_local >> 1); i += blockDim.x) {
+            const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+            const int hi = lo | j;
+            const bool asc = ((base + lo) & k) == 0;
+            const u64 a = d[lo], b = d[hi];
+            if ((a > b) == asc) { d[lo] = b; d[hi] = a; }
         }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p) {
+// one stage (merge size k, distance j >= SMEM_KEYS) over np keys in global memory; loads are batched ahead of the
+// compare-exchange so that a thread has eight independent pairs in flight instead of one
+__device__ __forceinline__ void bitonic_global_stage(u64* d, int np, int k, int j) {
+    constexpr int U = 8;
+    const int half = np >> 1;
+    for (int i0 = threadIdx.x; i0 < half; i0 += blockDim.x * U) {
+        u64 a[U], b[U];
+        int lo[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            lo[u] = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+            if (i < half) { a[u] = d[lo[u]]; b[u] = d[lo[u] | j]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            if (i < half) {
+                const bool asc = (lo[u] & k) == 0;
+                if ((a[u] > b[u]) == asc) { d[lo[u]] = b[u]; d[lo[u] | j] = a[u]; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Ascending sort of the n keys of one image (padded to np = pow2 with ~0).  Returns where the sorted keys live.
+__device__ u64* sort_keys(u64* gkeys, int n, int np, u64* skeys, int keys_in_smem) {
+    const int tid = threadIdx.x;
+    if (np <= keys_in_smem) {
+        for (int i = tid; i < np; i += blockDim.x) skeys[i] = i < n ? gkeys[i] : ~0ull;
+        __syncthreads();
+        for (int k = 2; k <= np; k <<= 1) bitonic_local(skeys, np, 0, k, k >> 1);
+        return skeys;
+    }
+    const int SEG = keys_in_smem;                       // np is a multiple of SEG (both powers of two)
+    for (int i = n + tid; i < np; i += blockDim.x) gkeys[i] = ~0ull;
+    __syncthreads();
+    // 1. every segment: all merge sizes up to SEG in shared memory
+    for (int s0 = 0; s0 < np; s0 += SEG) {
+        for (int i = tid; i < SEG; i += blockDim.x) skeys[i] = gkeys[s0 + i];
+        __syncthreads();
+        for (int k = 2; k <= SEG; k <<= 1) bitonic_local(skeys, SEG, s0, k, k >> 1);
+        for (int i = tid; i < SEG; i += blockDim.x) gkeys[s0 + i] = skeys[i];
+        __syncthreads();
+    }
+    // 2. larger merge sizes: the long-distance stages in global memory, the rest per segment in shared memory
+    for (int k = SEG << 1; k <= np; k <<= 1) {
+        for (int j = k >> 1; j >= SEG; j >>= 1) bitonic_global_stage(gkeys, np, k, j);
+        for (int s0 = 0; s0 < np; s0 += SEG) {
+            for (int i = tid; i < SEG; i += blockDim.x) skeys[i] = gkeys[s0 + i];
+            __syncthreads();
+            bitonic_local(skeys, SEG, s0, k, SEG >> 1);
+            for (int i = tid; i < SEG; i += blockDim.x) gkeys[s0 + i] = skeys[i];
+            __syncthreads();
+        }
+    }
+    return gkeys;
+}
+
+__global__ void __launch_bounds__(NT_SEL) nms_select_kernel(const SelectParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     // carve shared memory
     float4* cbox = reinterpret_cast<float4*>(smraw);                 // [CHUNK] offset boxes
@@ -202,34 +266,23 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
     int* canc = ccls + CHUNK;                                        // [CHUNK]
     int* kpos = canc + CHUNK;                                        // [CHUNK] chunk positions kept this round
     unsigned* alive_w = reinterpret_cast<unsigned*>(kpos + CHUNK);   // [CHUNK/32]
+    int* dead = reinterpret_cast<int*>(alive_w + CHUNK / 32);        // [CHUNK] suppressed by an earlier chunk's keeps
     __shared__ int s_newkept;
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n = min(p.ws.count[b], p.A);
     if (n == 0) { if (tid == 0) p.counts[b] = 0; return; }
     const int np = pow2ceil(n);
-    u64* gkeys = p.ws.keys + (size_t)b * p.ws.cap;
-    u64* keys;
-    if (np <= p.keys_in_smem) {
-        for (int i = tid; i < np; i += blockDim.x) skeys[i] = i < n ? gkeys[i] : ~0ull;
-        keys = skeys;
-    } else {
-        for (int i = n + tid; i < np; i += blockDim.x) gkeys[i] = ~0ull;
-        keys = gkeys;
-    }
-    __syncthreads();
-    bitonic_sort(keys, np);
+    const u64* keys = sort_keys(p.ws.keys + (size_t)b * p.ws.cap, n, np, skeys, p.keys_in_smem);
 
     const float scale = __fadd_rn(ord2f(p.ws.maxc[b]), 1.0f);
     const int rowf = 4 + p.nc;
     int kept = 0;
     for (int c0 = 0; c0 < n && kept < p.max_det; c0 += CHUNK) {
         const int cnt = min(CHUNK, n - c0);
-        // ---- 1. load this chunk's candidates ----
-        bool alive = tid < cnt;
-        float4 mine = make_float4(0.f, 0.f, 0.f, 0.f);
-        float marea = 0.f;
-        if (alive) {
+        // ---- 1. load this chunk's candidates (threads 0 .. cnt-1) ----
+        if (tid < CHUNK) dead[tid] = 0;
+        if (tid < cnt) {
             const u64 key = keys[c0 + tid];
             const int a = (int)(unsigned)(key & 0xffffffffu);
             const float conf = ord2f(~(unsigned)(key >> 32));
@@ -237,7 +290,7 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
             const float* row = p.pred + ((size_t)b * p.A + a) * rowf;
             const float4 bx = (p.nc & 3) ? make_float4(row[0], row[1], row[2], row[3]) : *reinterpret_cast<const float4*>(row);
             const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);
-            float4 u;
+            float4 u, mine;
             u.x = __fsub_rn(bx.x, hw); u.y = __fsub_rn(bx.y, hh); u.z = __fadd_rn(bx.x, hw); u.w = __fadd_rn(bx.y, hh);
             if (p.agnostic) mine = u;
             else {
@@ -245,22 +298,37 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
                 mine.x = __fadd_rn(u.x, off); mine.y = __fadd_rn(u.y, off);
                 mine.z = __fadd_rn(u.z, off); mine.w = __fadd_rn(u.w, off);
             }
-            marea = __fmul_rn(__fsub_rn(mine.z, mine.x), __fsub_rn(mine.w, mine.y));
-            ubox[tid] = u; cbox[tid] = mine; carea[tid] = marea; cconf[tid] = conf; ccls[tid] = cls; canc[tid] = a;
-            // ---- 2. against everything kept by earlier chunks ----
-            for (int k = 0; k < kept; ++k)
-                if (iou_gt(kbox[k], karea[k], mine, marea, p.iou)) { alive = false; break; }
+            ubox[tid] = u; cbox[tid] = mine;
+            carea[tid] = __fmul_rn(__fsub_rn(mine.z, mine.x), __fsub_rn(mine.w, mine.y));
+            cconf[tid] = conf; ccls[tid] = cls; canc[tid] = a;
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, alive);
-        if ((tid & 31) == 0) alive_w[tid >> 5] = bal;
+        __syncthreads();
+        // ---- 2. against everything kept by earlier chunks: two threads per candidate, each half of the kept list
+        //         (whether ANY kept box suppresses the candidate is all that matters, so the split is exact) ----
+        {
+            const int c = tid & (CHUNK - 1), part = tid >> 9;
+            if (c < cnt && kept > 0) {
+                const int mid = kept >> 1;
+                const int k0 = part ? mid : 0, k1 = part ? kept : mid;
+                const float4 mine = cbox[c];
+                const float marea = carea[c];
+                for (int k = k0; k < k1; ++k)
+                    if (iou_gt(kbox[k], karea[k], mine, marea, p.iou)) { dead[c] = 1; break; }
+            }
+        }
+        __syncthreads();
+        if (tid < CHUNK) {
+            const bool alive = tid < cnt && !dead[tid];
+            const unsigned bal = __ballot_sync(0xffffffffu, alive);
+            if ((tid & 31) == 0) alive_w[tid >> 5] = bal;
+        }
         __syncthreads();
         // ---- 3. in-chunk suppression bitmask (row i: later boxes j>i it would suppress) ----
-        // rows are dealt round-robin to the 16 warps; the 32 lanes of a warp test 32 columns at a time and a
-        // ballot yields the mask bits -- balanced work (the old one-thread-per-row loop left thread 0 with 511
-        // IoUs and thread 511 with none) and conflict-free shared-memory reads.
+        // rows are dealt round-robin to the 32 warps; the 32 lanes of a warp test 32 columns at a time and a
+        // ballot yields the mask bits -- balanced work and conflict-free shared-memory reads.
         {
             const int wid = tid >> 5, ln = tid & 31;
-            for (int i = wid; i < cnt; i += CHUNK / 32) {
+            for (int i = wid; i < cnt; i += NT_SEL / 32) {
                 if (!((alive_w[i >> 5] >> (i & 31)) & 1u)) continue;          // warp-uniform
                 const float4 bi = cbox[i];
                 const float ai = carea[i];
@@ -281,7 +349,7 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
             }
         }
         __syncthreads();
-        // ---- 4. serial resolution of the chunk ----
+        // ---- 4. serial resolution of the chunk: walk the set bits of (alive & ~removed) only ----
         if (tid == 0) {
             // `removed` lives in registers: the word loop is fully unrolled so every index is static
             u64 removed[CW];
@@ -292,16 +360,18 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
 #pragma unroll
             for (int w = 0; w < CW; ++w) {
                 if (full || w * 64 >= cnt) continue;
-                const u64 al = (u64)alive_w[2 * w] | ((u64)alive_w[2 * w + 1] << 32);
-                const int lim = min(64, cnt - w * 64);
-                for (int jj = 0; jj < lim; ++jj) {
-                    if (!((al >> jj) & 1ull) || ((removed[w] >> jj) & 1ull)) continue;
+                u64 cand = ((u64)alive_w[2 * w] | ((u64)alive_w[2 * w + 1] << 32)) & ~removed[w];
+                while (cand) {
+                    const int jj = __ffsll((long long)cand) - 1;
                     const int i = w * 64 + jj;
                     kpos[nk++] = i;
                     if (kept + nk >= p.max_det) { full = true; break; }
+                    const u64* mrow = mask + (size_t)i * CW;
 #pragma unroll
                     for (int v = 0; v < CW; ++v)
-                        if (v >= w) removed[v] |= mask[(size_t)i * CW + v];
+                        if (v >= w) removed[v] |= mrow[v];
+                    cand &= cand - 1;                    // this candidate is done
+                    cand &= ~removed[w];                 // and so is everything it (or an earlier keep) suppresses
                 }
             }
             s_newkept = nk;
@@ -333,7 +403,7 @@ __global__ void __launch_bounds__(CHUNK) nms_select_kernel(const SelectParams p)
 
 size_t select_smem_bytes(int max_det, int keys_in_smem) {
     return sizeof(float4) * (2 * CHUNK + (size_t)max_det) + sizeof(u64) * ((size_t)CHUNK * CW + keys_in_smem) +
-           sizeof(float) * (2 * CHUNK + (size_t)max_det) + sizeof(int) * (3 * CHUNK) + sizeof(unsigned) * (CHUNK / 32) + 64;
+           sizeof(float) * (2 * CHUNK + (size_t)max_det) + sizeof(int) * (4 * CHUNK) + sizeof(unsigned) * (CHUNK / 32) + 64;
 }
 
 NmsWs carve(void* ws, int B, int A) {
@@ -407,7 +477,7 @@ int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
             return YRE_OK;
         })) return e;
     if (smem > 200 * 1024) YRE_FAIL(YRE_EUNSUPPORTED, "nms: shared memory budget exceeded");
-    nms_select_kernel<<<d.B, CHUNK, smem, s>>>(sp);
+    nms_select_kernel<<<d.B, NT_SEL, smem, s>>>(sp);
     YRE_LAUNCH_CHECK("nms_select");
     return YRE_OK;
 }

@@ -455,12 +455,13 @@ def _weights_version(model: nn.Module) -> int:
     parameter and buffer.  Catches optimizer steps, ``load_state_dict``, ``p.copy_()``, ``p.data = new`` ...;
     writes THROUGH ``.data`` (``p.data.copy_()``, ``bias.data[:] = ...``) bump no counter and move no storage --
     after such an edit call ``model.invalidate()``."""
-    h = 0
-    for t in model.parameters():
-        h = hash((h, t.data_ptr(), t._version))
-    for t in model.buffers():
-        h = hash((h, t.data_ptr(), t._version))
-    return h
+    ts = model.__dict__.get("_wt_tensors")
+    if ts is None or len(ts[1]) != ts[0]:
+        # the module-tree walk is the expensive part (~1 ms for 937 tensors): do it once per structure
+        lst = list(model.parameters()) + list(model.buffers())
+        ts = (len(lst), lst)
+        model.__dict__["_wt_tensors"] = ts
+    return hash(tuple([(t.data_ptr(), t._version) for t in ts[1]]))
 
 
 def compile_model(model, x: torch.Tensor) -> Plan:

@@ -7,8 +7,13 @@ head: ``([y_aux, y_main], [raws_aux, raws_main])``), ``state_dict``-compatible w
 returned in TRAIN mode (model.py:163), ``detect.stride`` a plain tensor attribute.
 
 Differences by design: eval-mode forward is one replay of a pre-compiled libyre launch plan on the
-current CUDA stream (engine.py) instead of the named-DAG interpreter loop (model.py:87-107), and
-train-mode forward raises -- training is out of scope for this path.
+current CUDA stream (engine.py) instead of the named-DAG interpreter loop (model.py:87-107).
+Train-mode forward raises: in train mode the reference's BatchNorm layers normalise with BATCH statistics
+(blocks/conv.py:85, nn.BatchNorm2d in training mode) while the launch plan folds the RUNNING statistics into
+the weights, so handing back the plan's raw maps as the reference's train-mode output
+(heads/detect.py:84-85) would be silently wrong; training itself (loss, optimizer groups, EMA) is out of
+scope for this path.  Extension: ``forward`` also takes uint8 ``[B,H,W,3]`` BGR frames (cv2 layout) and fuses the
+host-side conversion of scripts/detect.py:223-227 into the first convolution.
 """
 from __future__ import annotations
 
@@ -120,8 +125,10 @@ class YOLO(nn.Module):
 
     # -- engine plumbing ------------------------------------------------------------------------
     def invalidate(self) -> None:
-        """Drops the compiled launch plans (weights changed / moved)."""
+        """Drops the compiled launch plans (weights changed / moved).  Call it after edits the per-forward check cannot
+        see: writes through ``.data`` and re-assignment of a whole ``nn.Parameter`` object."""
         self._plans.clear()
+        self.__dict__.pop("_wt_tensors", None)
 
     def set_precision(self, precision: str) -> "YOLO":
         if precision not in ("bf16", "fp32"):
@@ -133,6 +140,7 @@ class YOLO(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._plans = {}
+        self.__dict__.pop("_wt_tensors", None)
         return super()._apply(fn, *a, **k)
 
     def train(self, mode: bool = True):
@@ -142,8 +150,9 @@ class YOLO(nn.Module):
 
     def forward(self, x: torch.Tensor):
         if self.training:
-            raise NotImplementedError("train-mode forward is outside the B200 inference path; call .eval() "
-                                      "(YOLO.from_yaml returns the model in train mode, like the reference)")
+            raise NotImplementedError("train-mode forward is outside the B200 inference path (BatchNorm would need batch "
+                                      "statistics; the launch plan folds the running ones): call .eval() -- YOLO.from_yaml "
+                                      "returns the model in train mode, like the reference")
         from .engine import model_forward
         return model_forward(self, x)
 
@@ -186,20 +195,6 @@ class YOLO(nn.Module):
         detect.init_bias()
         self._stride_initialized = True
         self.train()
-
-    def optim_groups(self, weight_decay: float = 0.0005):
-        """src/yolo/model/model.py:165-203 (kept for API compatibility)."""
-        g_w, g_bn, g_b = [], [], []
-        for m in self.modules():
-            if hasattr(m, "bias") and isinstance(m.bias, nn.Parameter):
-                g_b.append(m.bias)
-            if isinstance(m, (nn.BatchNorm2d, nn.SyncBatchNorm, nn.GroupNorm)):
-                if isinstance(getattr(m, "weight", None), nn.Parameter):
-                    g_bn.append(m.weight)
-            elif isinstance(getattr(m, "weight", None), nn.Parameter):
-                g_w.append(m.weight)
-        return [{"params": g_w, "weight_decay": weight_decay}, {"params": g_bn, "weight_decay": 0.0},
-                {"params": g_b, "weight_decay": 0.0}]
 
     @classmethod
     def from_config(cls, config: ModelConfig, input_channels: int = 3) -> "YOLO":
