@@ -8,15 +8,16 @@
 //   nms_filter  HBM-bound pass over pred[B][A][4+nc]: per-anchor first-max class, strict
 //               `conf > thr` (+ optional class filter), xywh->xyxy, per-image max coordinate,
 //               compaction of (score, anchor) sort keys
-//   nms_select  one CTA (1024 threads) per image: bitonic sort of the 64-bit keys (== stable descending
-//               score sort, ties -> lower anchor first) -- in shared memory; above 8192 candidates the
-//               network is run segment-wise (8192-key segments sorted / merged in shared memory, only the
-//               few stages with a compare distance >= 8192 touch global memory) -- then a chunked greedy
-//               scan: every chunk of CHUNK sorted candidates is tested against the boxes kept so far
-//               (<= max_det of them, two threads per candidate), an IoU bitmask is built inside the chunk
-//               (32 warps), and one thread resolves the chunk by walking the set bits of the survivors.
-//               The scan stops as soon as max_det boxes are kept, which is exactly `keep[:max_det]` of the
-//               reference -- there is no pre-NMS top-k cap.
+//   nms_select  one CTA (1024 threads) per image: the candidates' 64-bit keys in ascending order (== stable
+//               descending score sort, ties -> lower anchor first) by a bitonic sort in shared memory; above
+//               8192 candidates only the best ~3000 are selected (threshold from a sorted sample) and sorted,
+//               because the scan below stops a few hundred candidates deep -- with an exact fallback to a
+//               full segmented sort.  Then a chunked greedy scan: every chunk of CHUNK sorted candidates is
+//               tested against the boxes kept so far (<= max_det, two threads per candidate), an IoU bitmask is
+//               built inside the chunk (32 warps; pairs of different classes are skipped where that is provably
+//               exact), and warp 0 resolves the chunk by walking the set bits of the survivors.  The scan stops
+//               as soon as max_det boxes are kept, which is exactly `keep[:max_det]` of the reference -- there
+//               is no pre-NMS top-k cap.
 //
 // Bit-exactness notes: every fp32 op is an explicitly rounded intrinsic (no FMA contraction);
 // the class offset is `float(cls) * (max_coord + 1)` then `box + offset` as two rounded ops
@@ -28,10 +29,28 @@ namespace {
 
 constexpr int CHUNK = 512;            // candidates per greedy round
 constexpr int NT_SEL = 1024;          // threads of nms_select (two per candidate of a chunk)
-constexpr int CW = CHUNK / 64;        // mask words per row
+constexpr int MW = CHUNK / 32;        // 32-bit mask words per row
 constexpr int SMEM_KEYS = 8192;       // keys sorted in shared memory at a time (one segment)
 
 typedef unsigned long long u64;
+
+// byte offsets of nms_select's fixed-size shared-memory arrays (the max_det-sized ones follow the key buffer)
+constexpr unsigned OFF_CBOX = 0, OFF_UBOX = OFF_CBOX + 16 * CHUNK, OFF_MASK = OFF_UBOX + 16 * CHUNK,
+                   OFF_AREA = OFF_MASK + 4 * CHUNK * MW, OFF_CONF = OFF_AREA + 4 * CHUNK, OFF_CLS = OFF_CONF + 4 * CHUNK,
+                   OFF_ANC = OFF_CLS + 4 * CHUNK, OFF_KPOS = OFF_ANC + 4 * CHUNK, OFF_DEAD = OFF_KPOS + 4 * CHUNK,
+                   OFF_INFO = OFF_DEAD + 4 * CHUNK, OFF_ALIVE = OFF_INFO + 4 * CHUNK, OFF_KEYS = OFF_ALIVE + 128,
+                   OFF_KBOX = OFF_KEYS + 8 * SMEM_KEYS;
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 __device__ __forceinline__ unsigned f2ord(float f) {   // order-preserving float -> uint
     const unsigned u = __float_as_uint(f);
@@ -50,6 +69,16 @@ struct NmsWs {           // carved out of the caller's workspace
 };
 
 __host__ __device__ inline int pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+#ifdef YRE_TUNING
+// tuning builds: SM-clock stamps of image 0's CTA at the phase boundaries of nms_select (yre_debug_nms_prof reads them)
+__device__ long long g_nms_prof[16];
+// (BAR.SYNC blocks lazily, at the first consumer of barrier-protected state: a volatile shared-memory read pins the stamp
+//  behind the barrier that precedes it)
+#define NMS_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { volatile int* vs = &s_newkept; long long t_ = clock64() + (long long)(*vs & 0); g_nms_prof[i] = t_; } } while (0)
+#else
+#define NMS_STAMP(i) do { } while (0)
+#endif
 
 __global__ void nms_init_kernel(int* count, unsigned* maxc, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,18 +191,32 @@ struct SelectParams {
     const float* pred; int B, A, nc; double iou; int max_det, agnostic;
     NmsWs ws;
     float* out; int* counts; long long* keep_anchor;
-    int keys_in_smem;     // SMEM_KEYS or 0
     const float* scale;   // optional [B][5] = pad_w, pad_h, gain, orig_w, orig_h (scale_boxes fused into the output)
+    float iou_lo, iou_hi; // iou * (1 -+ 2^-18) as floats: the division-free shortcut of iou_gt (0 / 0: shortcut off)
 };
 
-__device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const float4 b, const float ab, const double thr) {
+// thresholds of the division-free shortcut in iou_gt: thr * (1 -+ 2^-18) as floats, computed once on the host (as
+// kernel parameters they are constant-bank operands; derived in the kernel they were re-computed in fp64 at every use)
+struct IouThr { double thr; float lo, hi; bool quick, nonneg; };
+
+// IoU(a, b) > thr with the reference's arithmetic: inter / ((area_a + area_b) - inter) in fp32 (IEEE division), compared
+// against the threshold as a double.  The division (~45 issued instructions with its special-case path) is skipped when
+// the outcome is certain: an fp32 product and an fp32 quotient are each within 2^-24 of the exact value, so
+// inter < thr (1 - 2^-18) union implies quotient < thr and inter > thr (1 + 2^-18) union implies quotient > thr; only ratios
+// within 4e-6 of the threshold (and non-positive / tiny / NaN unions) take the exact path.
+__device__ __forceinline__ bool iou_gt(const float4 a, const float aa, const float4 b, const float ab, const IouThr t) {
     const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
     // inter == 0 -> IoU is +-0 or NaN, neither exceeds a threshold >= 0: skip the IEEE division (exact shortcut)
-    if (inter == 0.f && thr >= 0.0) return false;
-    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
-    return (double)iou > thr;
+    if (inter == 0.f && t.nonneg) return false;
+    const float uni = __fsub_rn(__fadd_rn(aa, ab), inter);
+    if (t.quick && uni > 1e-30f && uni < 1e30f) {
+        if (inter < __fmul_rn(t.lo, uni)) return false;
+        if (inter > __fmul_rn(t.hi, uni)) return true;
+    }
+    const float iou = __fdiv_rn(inter, uni);
+    return (double)iou > t.thr;
 }
 
 // bitonic network stages of merge size k with compare distances j = j_hi, j_hi/2, ..., 1 on the np_local keys in d
@@ -217,28 +260,30 @@ __device__ __forceinline__ void bitonic_global_stage(u64* d, int np, int k, int 
     __syncthreads();
 }
 
-// Ascending sort of the n keys of one image (padded to np = pow2 with ~0).  Returns where the sorted keys live.
-__device__ u64* sort_keys(u64* gkeys, int n, int np, u64* skeys, int keys_in_smem) {
+// ascending sort of m keys that already sit in shared memory (padded to a power of two with ~0)
+__device__ __forceinline__ void sort_smem(u64* skeys, int m) {
+    const int np = pow2ceil(m);
+    for (int i = m + threadIdx.x; i < np; i += blockDim.x) skeys[i] = ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= np; k <<= 1) bitonic_local(skeys, np, 0, k, k >> 1);
+}
+
+// Full ascending sort of n > keys_in_smem keys in global memory (padded to np = pow2 with ~0): the bitonic network run
+// segment-wise -- SEG-key segments are sorted / merged in shared memory, only the stages with a compare distance
+// >= SEG touch global memory.  Rarely needed (see top_keys).
+__device__ void sort_global(u64* gkeys, int n, u64* skeys, int SEG) {
     const int tid = threadIdx.x;
-    if (np <= keys_in_smem) {
-        for (int i = tid; i < np; i += blockDim.x) skeys[i] = i < n ? gkeys[i] : ~0ull;
-        __syncthreads();
-        for (int k = 2; k <= np; k <<= 1) bitonic_local(skeys, np, 0, k, k >> 1);
-        return skeys;
-    }
-    const int SEG = keys_in_smem;                       // np is a multiple of SEG (both powers of two)
+    const int np = pow2ceil(n);                          // a multiple of SEG (both powers of two)
     for (int i = n + tid; i < np; i += blockDim.x) gkeys[i] = ~0ull;
     __syncthreads();
-    // 1. every segment: all merge sizes up to SEG in shared memory
-    for (int s0 = 0; s0 < np; s0 += SEG) {
+    for (int s0 = 0; s0 < np; s0 += SEG) {               // every segment: all merge sizes up to SEG
         for (int i = tid; i < SEG; i += blockDim.x) skeys[i] = gkeys[s0 + i];
         __syncthreads();
         for (int k = 2; k <= SEG; k <<= 1) bitonic_local(skeys, SEG, s0, k, k >> 1);
         for (int i = tid; i < SEG; i += blockDim.x) gkeys[s0 + i] = skeys[i];
         __syncthreads();
     }
-    // 2. larger merge sizes: the long-distance stages in global memory, the rest per segment in shared memory
-    for (int k = SEG << 1; k <= np; k <<= 1) {
+    for (int k = SEG << 1; k <= np; k <<= 1) {           // larger merge sizes
         for (int j = k >> 1; j >= SEG; j >>= 1) bitonic_global_stage(gkeys, np, k, j);
         for (int s0 = 0; s0 < np; s0 += SEG) {
             for (int i = tid; i < SEG; i += blockDim.x) skeys[i] = gkeys[s0 + i];
@@ -248,38 +293,110 @@ __device__ u64* sort_keys(u64* gkeys, int n, int np, u64* skeys, int keys_in_sme
             __syncthreads();
         }
     }
-    return gkeys;
+}
+
+// The greedy scan stops after max_det keeps, i.e. a few hundred candidates deep (measured: rank 360-730 of up to 33 600),
+// so a full sort of a large candidate set is wasted work.  top_keys puts the SMALLEST m keys (= the m best candidates in
+// reference order), sorted, into shared memory: a threshold is read off a sorted sample of <= 4096 keys so that about
+// TARGET keys pass, those are compacted and sorted.  *partial tells the caller that candidates beyond the m exist; if the
+// scan runs out of the m before max_det boxes are kept it redoes the image on the fully sorted list (sort_global).
+constexpr int TOP_TARGET = 3072;
+__device__ int top_keys(const u64* gkeys, int n, u64* skeys, int keys_in_smem, int* s_cnt, bool* partial) {
+    const int tid = threadIdx.x;
+    if (n <= keys_in_smem) {
+        for (int i = tid; i < n; i += blockDim.x) skeys[i] = gkeys[i];
+        __syncthreads();
+        sort_smem(skeys, n);
+        *partial = false;
+        return n;
+    }
+    const int stride = (n + 4095) / 4096;
+    const int ns = (n + stride - 1) / stride;            // <= 4096 samples
+    for (int i = tid; i < ns; i += blockDim.x) skeys[i] = gkeys[(size_t)i * stride];
+    __syncthreads();
+    sort_smem(skeys, ns);
+    const u64 thr = skeys[min(ns - 1, TOP_TARGET / stride)];
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();                                      // every thread holds thr: the sample buffer can be reused
+    for (int i = tid; i < n; i += blockDim.x) {
+        const u64 k = gkeys[i];
+        if (k <= thr) {
+            const int pos = atomicAdd(s_cnt, 1);
+            if (pos < keys_in_smem) skeys[pos] = k;
+        }
+    }
+    __syncthreads();
+    const int m = *s_cnt;
+    if (m > keys_in_smem) return -1;                      // pathological score distribution: caller sorts everything
+    sort_smem(skeys, m);
+    *partial = m < n;
+    return m;
+}
+
+// packed (class, leaky) of a candidate -- see the cross-class shortcut in nms_select_kernel
+__device__ __forceinline__ bool may_overlap(int ia, int ib) {
+    const int ca = ia & 0x3fffffff, cb = ib & 0x3fffffff;
+    if (ca == cb) return true;
+    return ((ca > cb ? ia : ib) >> 30) & 1;               // the box of the HIGHER class must reach below -0.5 in x and y
 }
 
 __global__ void __launch_bounds__(NT_SEL) nms_select_kernel(const SelectParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    // carve shared memory
-    float4* cbox = reinterpret_cast<float4*>(smraw);                 // [CHUNK] offset boxes
-    float4* ubox = cbox + CHUNK;                                     // [CHUNK] plain boxes
-    float4* kbox = ubox + CHUNK;                                     // [max_det] kept offset boxes
-    u64* mask = reinterpret_cast<u64*>(kbox + p.max_det);            // [CHUNK][CW]
-    u64* skeys = mask + (size_t)CHUNK * CW;                          // [keys_in_smem]
-    float* carea = reinterpret_cast<float*>(skeys + p.keys_in_smem); // [CHUNK]
-    float* cconf = carea + CHUNK;                                    // [CHUNK]
-    float* karea = cconf + CHUNK;                                    // [max_det]
-    int* ccls = reinterpret_cast<int*>(karea + p.max_det);           // [CHUNK]
-    int* canc = ccls + CHUNK;                                        // [CHUNK]
-    int* kpos = canc + CHUNK;                                        // [CHUNK] chunk positions kept this round
-    unsigned* alive_w = reinterpret_cast<unsigned*>(kpos + CHUNK);   // [CHUNK/32]
-    int* dead = reinterpret_cast<int*>(alive_w + CHUNK / 32);        // [CHUNK] suppressed by an earlier chunk's keeps
-    __shared__ int s_newkept;
+    // carve shared memory.  Every array the inner loops touch sits at a COMPILE-TIME offset (fixed-size arrays first, the
+    // max_det-sized ones last): with run-time offsets and 64 registers per thread the compiler re-derived the bases from
+    // the kernel parameters inside the loops -- ~25 of the ~65 instructions per 32 pairs (ncu source view, profiles/).
+    float4* cbox = reinterpret_cast<float4*>(smraw + OFF_CBOX);      // [CHUNK] offset boxes
+    float4* ubox = reinterpret_cast<float4*>(smraw + OFF_UBOX);      // [CHUNK] plain boxes
+    unsigned* mask32 = reinterpret_cast<unsigned*>(smraw + OFF_MASK);// [CHUNK][MW] 32-bit mask words
+    float* carea = reinterpret_cast<float*>(smraw + OFF_AREA);       // [CHUNK]
+    float* cconf = reinterpret_cast<float*>(smraw + OFF_CONF);       // [CHUNK]
+    int* ccls = reinterpret_cast<int*>(smraw + OFF_CLS);             // [CHUNK]
+    int* canc = reinterpret_cast<int*>(smraw + OFF_ANC);             // [CHUNK]
+    int* kpos = reinterpret_cast<int*>(smraw + OFF_KPOS);            // [CHUNK] chunk positions kept this round
+    int* dead = reinterpret_cast<int*>(smraw + OFF_DEAD);            // [CHUNK] suppressed by an earlier chunk's keeps
+    int* cinfo = reinterpret_cast<int*>(smraw + OFF_INFO);           // [CHUNK] class | leaky << 30
+    unsigned* alive_w = reinterpret_cast<unsigned*>(smraw + OFF_ALIVE);   // [CHUNK/32]
+    u64* skeys = reinterpret_cast<u64*>(smraw + OFF_KEYS);           // [SMEM_KEYS]
+    float4* kbox = reinterpret_cast<float4*>(smraw + OFF_KBOX);      // [max_det] kept offset boxes
+    float* karea = reinterpret_cast<float*>(kbox + p.max_det);       // [max_det]
+    int* kinfo = reinterpret_cast<int*>(karea + p.max_det);          // [max_det]
+    // 32-bit shared address of the carve, made opaque so that it stays in ONE register (the compiler otherwise re-derives
+    // it from the cluster CTA id at every use): the mask phase addresses everything as sb + constant + index
+    unsigned sb = (unsigned)__cvta_generic_to_shared(smraw);
+    asm volatile("" : "+r"(sb));
+    __shared__ int s_newkept, s_cnt;
+    __shared__ bool s_partial;
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n = min(p.ws.count[b], p.A);
     if (n == 0) { if (tid == 0) p.counts[b] = 0; return; }
-    const int np = pow2ceil(n);
-    const u64* keys = sort_keys(p.ws.keys + (size_t)b * p.ws.cap, n, np, skeys, p.keys_in_smem);
+    u64* gkeys = p.ws.keys + (size_t)b * p.ws.cap;
+    NMS_STAMP(0);
+    int n_scan = top_keys(gkeys, n, skeys, SMEM_KEYS, &s_cnt, &s_partial);
+    __syncthreads();
+    bool partial = s_partial;
+    const u64* keys = skeys;
+    if (n_scan < 0) { sort_global(gkeys, n, skeys, SMEM_KEYS); keys = gkeys; n_scan = n; partial = false; }
+    NMS_STAMP(1);
 
     const float scale = __fadd_rn(ord2f(p.ws.maxc[b]), 1.0f);
+    // Cross-class shortcut (exact).  Class-aware NMS adds cls * scale to every coordinate (nms.py:79-81), scale = max
+    // coordinate + 1, so boxes of different classes sit in disjoint diagonal blocks -- unless a coordinate is negative
+    // enough to reach back into the previous class's block (the reference's leakage, which must be reproduced).  While
+    // nc * scale < 2^22 every rounding involved is <= 1/8: for classes c1 < c2 the two offsets differ by at least
+    // scale - 0.25, scale >= max coordinate + 0.875, and every x2 / y2 of class c1 is <= max coordinate; rounding is
+    // monotone, so the offset boxes can only intersect if the box of class c2 has x1 < -0.5 AND y1 < -0.5 ("leaky").
+    // Pairs of different classes whose higher-class box is not leaky have an empty intersection: IoU = 0, never
+    // suppressed, skipped without evaluating it.
+    IouThr ithr;
+    ithr.thr = p.iou; ithr.lo = p.iou_lo; ithr.hi = p.iou_hi; ithr.quick = p.iou_hi > 0.f; ithr.nonneg = p.iou >= 0.0;
+    const bool prune = !p.agnostic && __fmul_rn(__int2float_rn(p.nc), scale) < 4194304.f;
     const int rowf = 4 + p.nc;
     int kept = 0;
-    for (int c0 = 0; c0 < n && kept < p.max_det; c0 += CHUNK) {
-        const int cnt = min(CHUNK, n - c0);
+    for (int pass = 0; pass < 2; ++pass) {
+    kept = 0;
+    for (int c0 = 0; c0 < n_scan && kept < p.max_det; c0 += CHUNK) {
+        const int cnt = min(CHUNK, n_scan - c0);
         // ---- 1. load this chunk's candidates (threads 0 .. cnt-1) ----
         if (tid < CHUNK) dead[tid] = 0;
         if (tid < cnt) {
@@ -301,19 +418,24 @@ __global__ void __launch_bounds__(NT_SEL) nms_select_kernel(const SelectParams p
             ubox[tid] = u; cbox[tid] = mine;
             carea[tid] = __fmul_rn(__fsub_rn(mine.z, mine.x), __fsub_rn(mine.w, mine.y));
             cconf[tid] = conf; ccls[tid] = cls; canc[tid] = a;
+            cinfo[tid] = cls | ((u.x < -0.5f && u.y < -0.5f) ? (1 << 30) : 0);
         }
         __syncthreads();
+        if (c0 == 0) NMS_STAMP(2);
         // ---- 2. against everything kept by earlier chunks: two threads per candidate, each half of the kept list
         //         (whether ANY kept box suppresses the candidate is all that matters, so the split is exact) ----
         {
-            const int c = tid & (CHUNK - 1), part = tid >> 9;
+            constexpr int NPART = NT_SEL / CHUNK;
+            const int c = tid % CHUNK, part = tid / CHUNK;
             if (c < cnt && kept > 0) {
-                const int mid = kept >> 1;
-                const int k0 = part ? mid : 0, k1 = part ? kept : mid;
+                const int k0 = part * kept / NPART, k1 = (part + 1) * kept / NPART;
                 const float4 mine = cbox[c];
                 const float marea = carea[c];
-                for (int k = k0; k < k1; ++k)
-                    if (iou_gt(kbox[k], karea[k], mine, marea, p.iou)) { dead[c] = 1; break; }
+                const int mi = cinfo[c];
+                for (int k = k0; k < k1; ++k) {
+                    if (prune && !may_overlap(kinfo[k], mi)) continue;
+                    if (iou_gt(kbox[k], karea[k], mine, marea, ithr)) { dead[c] = 1; break; }
+                }
             }
         }
         __syncthreads();
@@ -323,65 +445,85 @@ __global__ void __launch_bounds__(NT_SEL) nms_select_kernel(const SelectParams p
             if ((tid & 31) == 0) alive_w[tid >> 5] = bal;
         }
         __syncthreads();
-        // ---- 3. in-chunk suppression bitmask (row i: later boxes j>i it would suppress) ----
-        // rows are dealt round-robin to the 32 warps; the 32 lanes of a warp test 32 columns at a time and a
-        // ballot yields the mask bits -- balanced work and conflict-free shared-memory reads.
+        if (c0 == 0) NMS_STAMP(3);
+        // ---- 3. in-chunk suppression bitmask (row i: later boxes j > i it would suppress), 32-bit words ----
+        // The lower triangle is cut into 32 x 32 tiles (column block cb, row block rb <= cb), dealt round-robin to the 32
+        // warps.  In a tile every lane owns ONE column -- box / area / class held in registers -- and the warp walks the 32
+        // rows: a few broadcast shared-memory loads per row, the IoU test against the lane's own column, one ballot = one
+        // mask word.  (The first version walked columns per row with per-lane index arithmetic and loads: ~90 issued
+        // instructions per 32 pairs, now ~45; dealing whole column blocks to warps left the last warp with 16x the work
+        // of the first.  Measured alternatives that lost: two rows per turn (spills at 64 registers), a branch-free
+        // classification (gives up the class shortcut), 512 threads with 128 registers (fewer warps to hide the
+        // ~400-cycle dependent chain of a row).)
         {
             const int wid = tid >> 5, ln = tid & 31;
-            for (int i = wid; i < cnt; i += NT_SEL / 32) {
-                if (!((alive_w[i >> 5] >> (i & 31)) & 1u)) continue;          // warp-uniform
-                const float4 bi = cbox[i];
-                const float ai = carea[i];
-                for (int w = i >> 6; w < CW; ++w) {
-                    unsigned lo_bits = 0u, hi_bits = 0u;
-                    if (w * 64 < cnt) {
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int j = w * 64 + h * 32 + ln;
-                            bool sup = false;
-                            if (j > i && j < cnt && ((alive_w[j >> 5] >> (j & 31)) & 1u)) sup = iou_gt(bi, ai, cbox[j], carea[j], p.iou);
-                            const unsigned bal2 = __ballot_sync(0xffffffffu, sup);
-                            if (h == 0) lo_bits = bal2; else hi_bits = bal2;
-                        }
+            const int nb = (cnt + 31) >> 5;                           // 32-candidate blocks in this chunk
+            const int ntile = nb * (nb + 1) / 2;
+            for (int t = wid; t < ntile; t += NT_SEL / 32) {
+                int cb = 0;
+                while ((cb + 1) * (cb + 2) / 2 <= t) ++cb;            // tile t -> (cb, rb), rb <= cb
+                int rb = t - cb * (cb + 1) / 2;
+                asm volatile("" : "+r"(rb), "+r"(cb));                // keep them in registers (not re-derived per row)
+                const int j = cb * 32 + ln;
+                const bool jv = j < cnt && ((lds32(sb + OFF_ALIVE + 4u * cb) >> ln) & 1u);
+                float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+                float aj = 0.f;
+                int ij = 0;
+                if (jv) { bj = lds128(sb + OFF_CBOX + 16u * j); aj = __uint_as_float(lds32(sb + OFF_AREA + 4u * j)); ij = (int)lds32(sb + OFF_INFO + 4u * j); }
+                unsigned rows = lds32(sb + OFF_ALIVE + 4u * rb);      // alive rows of the block (rows >= cnt are not alive)
+                const unsigned a_mask = sb + OFF_MASK + 4u * (unsigned)cb;
+                while (rows) {                                        // warp-uniform walk over the alive rows
+                    const int i = rb * 32 + __ffs((int)rows) - 1;
+                    rows &= rows - 1;
+                    bool sup = false;
+                    if (jv && j > i) {
+                        const int ii = (int)lds32(sb + OFF_INFO + 4u * i);
+                        if (!prune || may_overlap(ii, ij))
+                            sup = iou_gt(lds128(sb + OFF_CBOX + 16u * i), __uint_as_float(lds32(sb + OFF_AREA + 4u * i)), bj, aj, ithr);
                     }
-                    if (ln == 0) mask[(size_t)i * CW + w] = (u64)lo_bits | ((u64)hi_bits << 32);
+                    const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                    if (ln == 0) sts32(a_mask + 4u * MW * (unsigned)i, bal);
                 }
             }
         }
         __syncthreads();
-        // ---- 4. serial resolution of the chunk: walk the set bits of (alive & ~removed) only ----
-        if (tid == 0) {
-            // `removed` lives in registers: the word loop is fully unrolled so every index is static
-            u64 removed[CW];
-#pragma unroll
-            for (int w = 0; w < CW; ++w) removed[w] = 0ull;
+        if (c0 == 0) NMS_STAMP(4);
+        // ---- 4. resolution of the chunk by warp 0: walk the set bits of (alive & ~removed) of one 32-candidate word at a
+        //         time.  Every lane tracks the current word (same value in all lanes, no shuffle in the loop); lane v also
+        //         accumulates word v of the removed set for the words still to come.  ~120 cycles per kept box
+        //         (scripts/ubench/resolve_loop.cu), against ~160 for one thread with the whole set in its registers. ----
+        if (tid < 32) {
+            const int ln = tid, nw = (cnt + 31) >> 5;
+            unsigned removed_own = 0u;                                // lane v < nw: word v of the removed set
             int nk = 0;
             bool full = false;
-#pragma unroll
-            for (int w = 0; w < CW; ++w) {
-                if (full || w * 64 >= cnt) continue;
-                u64 cand = ((u64)alive_w[2 * w] | ((u64)alive_w[2 * w + 1] << 32)) & ~removed[w];
+            for (int w = 0; w < nw && !full; ++w) {
+                unsigned rem_w = __shfl_sync(0xffffffffu, removed_own, w);
+                unsigned cand = alive_w[w] & ~rem_w;
                 while (cand) {
-                    const int jj = __ffsll((long long)cand) - 1;
-                    const int i = w * 64 + jj;
-                    kpos[nk++] = i;
+                    const int i = w * 32 + __ffs((int)cand) - 1;
+                    if (ln == 0) kpos[nk] = i;
+                    ++nk;
                     if (kept + nk >= p.max_det) { full = true; break; }
-                    const u64* mrow = mask + (size_t)i * CW;
-#pragma unroll
-                    for (int v = 0; v < CW; ++v)
-                        if (v >= w) removed[v] |= mrow[v];
-                    cand &= cand - 1;                    // this candidate is done
-                    cand &= ~removed[w];                 // and so is everything it (or an earlier keep) suppresses
+                    const unsigned* mrow = mask32 + i * MW;
+                    rem_w |= mrow[w];                                 // broadcast load: the word being walked
+                    if (ln > w && ln < nw) removed_own |= mrow[ln];   // the later words, one per lane
+                    cand &= cand - 1;                                 // this candidate is done
+                    cand &= ~rem_w;                                   // and so is everything a keep suppresses
                 }
             }
-            s_newkept = nk;
+            if (ln == 0) s_newkept = nk;
+#ifdef YRE_TUNING
+            if (c0 == 0 && blockIdx.x == 0 && ln == 0) { g_nms_prof[8] = clock64(); g_nms_prof[9] = nk; g_nms_prof[10] = cnt; }
+#endif
         }
         __syncthreads();
+        if (c0 == 0) NMS_STAMP(5);
         // ---- 5. publish the newly kept boxes ----
         const int nk = s_newkept;
         for (int q = tid; q < nk; q += blockDim.x) {
             const int i = kpos[q], k = kept + q;
-            kbox[k] = cbox[i]; karea[k] = carea[i];
+            kbox[k] = cbox[i]; karea[k] = carea[i]; kinfo[k] = cinfo[i];
             float* o = p.out + ((size_t)b * p.max_det + k) * 6;
             float4 u = ubox[i];
             if (p.scale) {        // scale_boxes (scripts/detect.py:74-109), same ops as scale_boxes_kernel (k_preproc.cu)
@@ -397,13 +539,20 @@ __global__ void __launch_bounds__(NT_SEL) nms_select_kernel(const SelectParams p
         }
         kept += nk;
         __syncthreads();
+        if (c0 == 0) NMS_STAMP(6);
     }
+    // the best TOP_TARGET candidates did not yield max_det boxes and there are more: redo the image on the full sorted list
+    if (!(partial && kept < p.max_det)) break;
+    sort_global(gkeys, n, skeys, SMEM_KEYS);
+    keys = gkeys; n_scan = n; partial = false;
+    }
+    NMS_STAMP(7);
     if (tid == 0) p.counts[b] = kept;
 }
 
-size_t select_smem_bytes(int max_det, int keys_in_smem) {
-    return sizeof(float4) * (2 * CHUNK + (size_t)max_det) + sizeof(u64) * ((size_t)CHUNK * CW + keys_in_smem) +
-           sizeof(float) * (2 * CHUNK + (size_t)max_det) + sizeof(int) * (4 * CHUNK) + sizeof(unsigned) * (CHUNK / 32) + 64;
+size_t select_smem_bytes(int max_det) {
+    return sizeof(float4) * (2 * CHUNK + (size_t)max_det) + sizeof(unsigned) * ((size_t)CHUNK * MW + 32) + sizeof(u64) * SMEM_KEYS +
+           sizeof(float) * (2 * CHUNK + (size_t)max_det) + sizeof(int) * (5 * CHUNK + (size_t)max_det) + 64;
 }
 
 NmsWs carve(void* ws, int B, int A) {
@@ -468,9 +617,13 @@ int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
     sp.pred = d.pred; sp.B = d.B; sp.A = d.A; sp.nc = d.nc; sp.iou = d.iou_thres; sp.max_det = d.max_det;
     sp.agnostic = d.agnostic; sp.ws = ws; sp.out = d.out; sp.counts = d.counts;
     sp.keep_anchor = reinterpret_cast<long long*>(d.keep_anchor);
-    sp.keys_in_smem = SMEM_KEYS;
     sp.scale = d.scale;
-    const size_t smem = select_smem_bytes(d.max_det, SMEM_KEYS);
+    sp.iou_lo = sp.iou_hi = 0.f;
+    if (d.iou_thres > 1e-6 && d.iou_thres < 1e6) {
+        sp.iou_lo = (float)(d.iou_thres * (1.0 - 1.0 / 262144.0));
+        sp.iou_hi = (float)(d.iou_thres * (1.0 + 1.0 / 262144.0));
+    }
+    const size_t smem = select_smem_bytes(d.max_det);
     static YrePerDeviceOnce once;
     if (int e = once.run([]() -> int {
             YRE_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -481,3 +634,10 @@ int launch_nms(const yre_nms_desc& d, cudaStream_t s) {
     YRE_LAUNCH_CHECK("nms_select");
     return YRE_OK;
 }
+
+#ifdef YRE_TUNING
+extern "C" int yre_debug_nms_prof(long long* host16) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(host16, g_nms_prof, sizeof(long long) * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
