@@ -388,6 +388,43 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- bf16 accuracy in detection terms (rank 0, first 8 images): final detections of the bf16 product path against the
+    #      fp32 validation engine's (same class, IoU >= 0.9).  The calibrated RANDOM-weight network is chaotic,
+    #      so the end-to-end figure is low for any bf16 implementation; tests/test_gpu_round2.py holds the gated statements
+    #      (teacher-forced head >= 0.90, end to end relative to the reference graph run in bf16).
+    det_agree = None
+    if not args.quick:
+        try:
+            import numpy as np
+            nb = min(8, Bn)
+            m32 = YOLO.from_yaml(yaml_path)
+            m32.load_state_dict(sd, strict=True)
+            m32 = m32.to(dev).eval().set_precision("fp32")
+            m32.main_only = bool(args.main_only)
+            y32, _ = m32(x_dev[:nb].contiguous())
+            if isinstance(y32, (list, tuple)):
+                y32 = y32[1]
+            d32 = [d.cpu().numpy() for d in non_max_suppression(y32.permute(0, 2, 1), CONF, IOU, MAX_DET)]
+            d16 = [d.cpu().numpy() for d in dets[:nb]]
+
+            def frac(ref, got):
+                if len(ref) == 0:
+                    return 1.0
+                if len(got) == 0:
+                    return 0.0
+                x1 = np.maximum(ref[:, None, 0], got[None, :, 0]); y1 = np.maximum(ref[:, None, 1], got[None, :, 1])
+                x2 = np.minimum(ref[:, None, 2], got[None, :, 2]); y2 = np.minimum(ref[:, None, 3], got[None, :, 3])
+                inter = np.clip(x2 - x1, 0, None) * np.clip(y2 - y1, 0, None)
+                ar = (ref[:, 2] - ref[:, 0]) * (ref[:, 3] - ref[:, 1]); ag = (got[:, 2] - got[:, 0]) * (got[:, 3] - got[:, 1])
+                iou = inter / (ar[:, None] + ag[None, :] - inter + 1e-12)
+                return float(((iou >= 0.9) & (ref[:, None, 5] == got[None, :, 5])).any(1).mean())
+            det_agree = {"images": nb, "fp32_detections_matched_by_bf16": float(np.mean([frac(a, b) for a, b in zip(d32, d16)])),
+                         "bf16_detections_matched_by_fp32": float(np.mean([frac(b, a) for a, b in zip(d32, d16)])),
+                         "note": "end to end on a chaotic random-weight network; gated statements: tests/test_gpu_round2.py"}
+            del m32
+        except Exception as e:
+            det_agree = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     # ---- NMS device time: whole (3 launches) and the HBM-bound candidate pass alone ----
     pred_static = pred_of(x_dev).contiguous()
     torch.cuda.synchronize(dev)
@@ -532,7 +569,8 @@ def main():
                    "l2": f"input batch ({x_host.numel() * 4 / 1e6:.0f} MB fp32) and activations exceed the 126 MB L2",
                    "detections_per_image": dets_per_img, "parallelism": f"image-sharded x{world}, no data-path collective",
                    "value_definition": "YOLO.forward + non_max_suppression_async().result() (counts D2H + list slicing), one batch in flight",
-                   "value_no_host_sync": value_nosync, "value_default_flags": default_flags},
+                   "value_no_host_sync": value_nosync, "value_default_flags": default_flags,
+                   "bf16_detection_agreement": det_agree},
         "e2e": e2e, "e2e_fp32_input": e2e_f32,
         "host_cores_bound": (len(numa_cpus) if numa_cpus else None),
         "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,

@@ -61,8 +61,8 @@ def run(Bn, H, W, Cin, Cout, k):
         seq = [(t - t0, ev) for t, r, ev in evs if r == role]
         seq.sort()
         line = []
-        prev = seq[-45][0] if len(seq) > 44 else 0
-        for t, ev in seq[-44:]:
+        prev = seq[-61][0] if len(seq) > 60 else 0
+        for t, ev in seq[-60:]:
             line.append(f"{NAMES[ev]}@{t}(+{t - prev})")
             prev = t
         print(" role", role, " ".join(line))
@@ -70,6 +70,6 @@ def run(Bn, H, W, Cin, Cout, k):
 
 shapes = [(8, 160, 160, 32, 32, 3), (8, 160, 160, 64, 64, 1), (8, 80, 80, 128, 128, 3), (8, 80, 80, 256, 256, 3)]
 if len(sys.argv) > 1 and sys.argv[1] == 'mem':
-    shapes = [(64, 80, 80, 128, 128, 1), (64, 160, 160, 64, 64, 1), (64, 40, 40, 256, 256, 1), (64, 160, 160, 32, 32, 3), (64, 80, 80, 64, 64, 3)]
+    shapes = [(64, 80, 80, 128, 128, 1), (64, 40, 40, 256, 256, 1), (64, 40, 40, 1024, 512, 1)]
 for shape in shapes:
     run(*shape)

@@ -434,7 +434,13 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             // to the TMA unit is warp-uniform, so the issue stays on the uniform datapath (no per-lane serialising loop).
             auto process32 = [&](const uint32_t* w, int col, bool more) {
                 float f[32];
+#ifdef YRE_TUNING
+                if (tracer) trace(p.dbg, 2, tn, 23);
+#endif
                 epilogue_math<32>(p, sbias, w, f, valid, pix, n0 + col, res16 ? rr : nullptr);
+#ifdef YRE_TUNING
+                if (tracer) trace(p.dbg, 2, tn, 24);
+#endif
                 if (res16 && more) {                      // this group's next full chunk of the tile
 #pragma unroll
                     for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + col + 32 * CS + 8 * i);
@@ -442,6 +448,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
                 if (tma_store) {
                     if (elect_one()) bulk_wait_read<1>();       // the store that used this buffer two chunks ago has read it
                     __syncwarp();
+#ifdef YRE_TUNING
+                    if (tracer) trace(p.dbg, 2, tn, 25);
+#endif
                     const uint32_t buf = stg + obuf * stage_out;
                     store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
                     fence_async_smem();
@@ -450,6 +459,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
                         tma_store_4d(tmY, buf, y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
                         bulk_commit();
                     }
+#ifdef YRE_TUNING
+                    if (tracer) trace(p.dbg, 2, tn, 26);
+#endif
                     obuf ^= 1u;
                 } else if (valid) {
                     store_direct<32>(p, f, pix, n0 + col);
