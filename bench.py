@@ -224,6 +224,7 @@ def main():
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).eval().set_precision(args.precision)
     model.main_only = bool(args.main_only)
+    model.fuse_upsample = os.environ.get("YRE_BENCH_FUSE_UP", "1") != "0"    # A/B switch: 0 runs the Upsample layers as kernels
     model.check_weights = False
     model.fresh_outputs = False
     model.use_cuda_graph = os.environ.get("YRE_BENCH_GRAPH", "1") != "0"     # static buffers -> the forward replays as one CUDA graph

@@ -72,12 +72,22 @@ int         yre_device_check(void);
  * engine: YRE_ENGINE_TCGEN05 = implicit-GEMM on tcgen05/TMEM with TMA-staged operands
  * (bf16 x/w, Cin%32==0, Cout%16==0, stride-2 needs a YRE_PHASE4 input);
  * YRE_ENGINE_FFMA = fp32-accurate SIMT implicit GEMM (the fp32 validation mode and the
- * fallback for shapes tcgen05 does not take); YRE_ENGINE_AUTO picks tcgen05 when eligible. */
+ * fallback for shapes tcgen05 does not take); YRE_ENGINE_AUTO picks tcgen05 when eligible.
+ *
+ * xu (optional, xu.ptr != NULL; 1x1 stride-1 convs only): a HALF-resolution view [B][H/2][W/2] whose 2x nearest-neighbour
+ * upsample supplies the FIRST xu.C input channels, x the remaining x.C -- i.e. the conv reads
+ * cat([Upsample(2, nearest)(xu), x], dim=channels) without that tensor ever being written:
+ *   nn.Upsample + Concat + the consumer's 1x1 conv   src/yolo/model/parser.py:159-171, src/yolo/blocks/common.py:32-33,
+ *                                                     src/yolo/blocks/gelan.py:58 (conv_in of the neck's RepNCSPELAN4)
+ * w is then [Cout][1][1][xu.C + x.C].  On the tcgen05 engine the upsample is a TMA addressing mode (a tensor map over xu
+ * whose two duplicated dimensions have global stride 0); results are bit-identical to running the conv on the
+ * materialised concat. */
 typedef struct yre_conv_desc {
     yre_view    x, y, res;  /* res.ptr == NULL: no residual; res has y's shape */
     const void* w;
     const float* bias;
     int32_t     k, stride, act, engine;
+    yre_view    xu;         /* xu.ptr == NULL: plain conv */
 } yre_conv_desc;
 int yre_conv(const yre_conv_desc* d, yre_stream_t s);
 

@@ -49,6 +49,8 @@ def run(plan) -> None:
     for kind, a in plan.trace:
         if kind == "conv":
             x = nchw(read(a["x"]))
+            if a.get("xu") is not None:                     # yre_conv_desc.xu: cat([upsample2x(xu), x]) read in place
+                x = torch.cat((F.interpolate(nchw(read(a["xu"])), scale_factor=2.0, mode="nearest"), x), 1)
             w = a["w"].float().permute(0, 3, 1, 2)          # [Cout][kh][kw][Cin] -> OIHW
             y = F.conv2d(x, w, a["b"].float(), a["stride"], a["k"] // 2)
             if a["silu"]:

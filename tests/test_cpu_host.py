@@ -97,10 +97,11 @@ def test_gelan_c_plan_wiring(gelan_c, dry, prec):
     y_ref, raws_ref = G.forward(nodes, nc, sd, x, capture=cap)
     p = engine.compile_model(m, x)
     census = Counter(n for n, _ in p.op_table())
-    # 8 ELAN blocks x 12 fused convs + 5 ADown x 2 + SPP 2 + stem2 + 3 levels x 5 head convs = 124
-    assert census == {"conv_ffma": 124, "adown_prepool": 5, "upsample2x": 2, "stem": 1, "spp_maxpool": 1,
-                      "dfl_decode_score": 1}, census
-    assert p.num_launches == 134
+    # 8 ELAN blocks x 12 fused convs + 5 ADown x 2 + SPP 2 + stem2 + 3 levels x 5 head convs = 124; the two Upsample
+    # layers emit nothing: their consumers' 1x1 convs read the half-resolution maps (yre_conv_desc.xu)
+    assert census == {"conv_ffma": 124, "adown_prepool": 5, "stem": 1, "spp_maxpool": 1, "dfl_decode_score": 1}, census
+    assert p.num_launches == 132
+    assert sum(1 for k, a in p.trace if k == "conv" and a.get("xu") is not None) == 2
     gf = sum(f for _, f in p.op_table()) / 1e9
     assert abs(gf - 102.136 * (128 / 640) ** 2 * 1.0) / gf < 0.06      # folded-graph FLOPs (+ dense-expanded head groups)
     X.run(p)

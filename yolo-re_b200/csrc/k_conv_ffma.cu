@@ -11,7 +11,8 @@
 namespace {
 
 struct FfmaParams {
-    DView x, y, res;
+    DView x, y, res, xu;     // xu: optional half-resolution source of the first Cu input channels (2x nearest upsample)
+    int Cu;
     const void* w;
     const float* bias;
     int k, stride, pad, act, has_res;
@@ -58,10 +59,12 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const FfmaParams p) {
         const int iy = loy * p.stride + dy - p.pad, ix = lox * p.stride + dx - p.pad;
         const bool inb = lvalid && iy >= 0 && iy < p.x.H && ix >= 0 && ix < p.x.W;
         const long long xbase = inb ? dview_pix(p.x, lb, iy, ix) : 0;
+        const long long ubase = (inb && p.Cu) ? dview_pix(p.xu, lb, iy >> 1, ix >> 1) : 0;   // 1x1 only: nearest source pixel
         const long long wbase = ((long long)ln * taps + tap) * p.Cin;
         for (int c0 = 0; c0 < p.Cin; c0 += TK) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-            if (inb && c0 + lk < p.Cin) a = ld4<TIn>(p.x.ptr, xbase + c0 + lk);
+            if (inb && c0 + lk < p.Cin)
+                a = (c0 + lk < p.Cu) ? ld4<TIn>(p.xu.ptr, ubase + c0 + lk) : ld4<TIn>(p.x.ptr, xbase + c0 + lk - p.Cu);
             if (nvalid && c0 + lk < p.Cin) b = ld4<TIn>(p.w, wbase + c0 + lk);
             __syncthreads();
             As[lk + 0][lrow] = a.x; As[lk + 1][lrow] = a.y; As[lk + 2][lrow] = a.z; As[lk + 3][lrow] = a.w;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(256) conv_ffma_kernel(const FfmaParams p) {
 }  // namespace
 
 double conv_flops(const yre_conv_desc& d) {
-    return 2.0 * d.y.B * d.y.H * d.y.W * (double)d.y.C * d.x.C * d.k * d.k;
+    return 2.0 * d.y.B * d.y.H * d.y.W * (double)d.y.C * (d.x.C + (d.xu.ptr ? d.xu.C : 0)) * d.k * d.k;
 }
 
 int launch_conv_ffma(const yre_conv_desc& d, cudaStream_t s) {
@@ -123,6 +126,11 @@ int launch_conv_ffma(const yre_conv_desc& d, cudaStream_t s) {
     p.res = p.has_res ? make_dview(d.res) : p.y;
     p.w = d.w; p.bias = d.bias; p.k = d.k; p.stride = d.stride; p.pad = d.k / 2; p.act = d.act;
     p.Ho = d.y.H; p.Wo = d.y.W; p.Cin = d.x.C; p.Cout = d.y.C;
+    p.xu = p.x; p.Cu = 0;
+    if (d.xu.ptr) {
+        if (d.xu.C % 4 || d.xu.c_off % 4 || d.xu.C_total % 4) YRE_FAIL(YRE_EUNSUPPORTED, "conv_ffma: channel counts/offsets must be multiples of 4");
+        p.xu = make_dview(d.xu); p.Cu = d.xu.C; p.Cin += p.Cu;
+    }
     p.M = (long long)d.y.B * d.y.H * d.y.W;
     if (p.Cin % 4 || p.Cout % 4 || d.x.c_off % 4 || d.y.c_off % 4 || d.x.C_total % 4 || d.y.C_total % 4 ||
         (p.has_res && (d.res.c_off % 4 || d.res.C_total % 4)))

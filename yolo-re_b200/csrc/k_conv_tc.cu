@@ -78,6 +78,10 @@ struct TcParams {
     // M tiles 2 * (u / tiles_n) + {0, 1} (cluster rank); each CTA stages its own 128-pixel A tile and block_n / 2 rows of
     // the weight tile, the leader issues 256 x block_n MMAs.  num_units = tiles_n * ceil(mtiles / 2).
     int cta2;
+    // virtual cat([upsample2x(xu), x]) input of a 1x1 conv (yre_conv_desc::xu): the first ku_chunks K chunks come from the
+    // half-resolution tensor through tmAu -- dims {C, 2, W/2, 2, (H/2) * B} with the two "2" dimensions at global stride 0,
+    // so one box {block_k, 2, tw/2, 2, th/2} delivers the tw x th patch of the UPSAMPLED map in the usual row order
+    int ku_chunks, xu_coff, xu_rows;      // xu_rows = H/2 (rows of one image in the merged row dimension)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -528,7 +532,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
 template <int KSTEPS, int NT, bool CTA2>
 __global__ void __launch_bounds__(NT, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAu, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents();
     if (p.dbg && threadIdx.x == 0) {       // trace mode: per-CTA entry stamp (globaltimer ns, SM clock)
@@ -558,7 +562,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int wstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int wtotal = CTA2 ? p.num_units : p.num_tiles;
 
-    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); if (p.tma_store) tma_prefetch_desc(&tmY); }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); if (p.tma_store) tma_prefetch_desc(&tmY); if (p.ku_chunks) tma_prefetch_desc(&tmAu); }
     if (warp == 1 && lane == 0) {
         // the leader's tmem_empty barriers collect the epilogue warps of BOTH CTAs of a pair
         const uint32_t n_epi = 4u * (uint32_t)p.csplit * (CTA2 ? 2u : 1u);
@@ -622,16 +626,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (pipe == 0 && lane == 0) trace(p.dbg, 0, tn, 1);
                     if (elect_one()) {
                         const uint32_t sa = sbase + gs * stage_bytes, sb = sa + p.a_bytes;
-                        const int c = p.x_coff + kc * p.block_k;
+                        const bool up = kc < p.ku_chunks;          // this K chunk comes from the upsampled half-resolution source
+                        const int c = up ? p.xu_coff + kc * p.block_k : p.x_coff + (kc - p.ku_chunks) * p.block_k;
+                        const uint32_t img_bytes = p.a_bytes / (uint32_t)p.tb;      // one image's tw x th rows of the A tile
                         if (CTA2) {
                             // both CTAs' boxes complete on the leader's barrier, which expects the pair's bytes
                             if (rank == 0) mbar_expect_tx(full, 2u * stage_bytes);
-                            if (p.phase4) tma_load_5d_cg2(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
+                            if (up) {
+                                for (int i = 0; i < p.tb; ++i)
+                                    tma_load_5d_cg2(sa + (uint32_t)i * img_bytes, &tmAu, full, c, 0, x0 >> 1, 0, (b0 + i) * p.xu_rows + (y0 >> 1));
+                            }
+                            else if (p.phase4) tma_load_5d_cg2(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
                             else tma_load_4d_cg2(sa, &tmA, full, c, x0 + dx, y0 + dy, b0);
                             tma_load_2d_cg2(sb, &tmB, full, tap * p.Cin + kc * p.block_k, n0);
                         } else {
                             mbar_expect_tx(full, stage_bytes);
-                            if (p.phase4) tma_load_5d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
+                            if (up) {
+                                for (int i = 0; i < p.tb; ++i)
+                                    tma_load_5d(sa + (uint32_t)i * img_bytes, &tmAu, full, c, 0, x0 >> 1, 0, (b0 + i) * p.xu_rows + (y0 >> 1));
+                            }
+                            else if (p.phase4) tma_load_5d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0, plane);
                             else tma_load_4d(sa, &tmA, full, c, x0 + dx, y0 + dy, b0);
                             tma_load_2d(sb, &tmB, full, tap * p.Cin + kc * p.block_k, n0);
                         }
@@ -732,7 +746,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int KSTEPS, int COUT>
 __global__ void __launch_bounds__(NT_3WG, 1)
 conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmY, const TcParams p) {
+                  const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap /*tmAu: generic kernel only*/, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents();
     if (p.dbg && threadIdx.x == 0) {       // trace mode: per-CTA entry stamp (globaltimer ns, SM clock)
@@ -865,7 +879,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 template <int NT>
 __global__ void __launch_bounds__(NT, 1)
 conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmY, const TcParams p) {
+                         const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap /*tmAu: generic kernel only*/, const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     pdl_launch_dependents();
     if (p.dbg && threadIdx.x == 0) {
@@ -1057,7 +1071,7 @@ int env_int(const char* name, int dflt) {
 }  // namespace
 
 struct ConvTcPlan {
-    CUtensorMap tmA, tmB, tmY;
+    CUtensorMap tmA, tmB, tmY, tmAu;
     TcParams p;
     int grid;
     size_t smem;
@@ -1081,7 +1095,7 @@ static cudaError_t launch_tc(K kernel, int grid, int block, size_t smem, cudaStr
         ++n;
     }
     cfg.attrs = at; cfg.numAttrs = n;
-    return cudaLaunchKernelEx(&cfg, kernel, pl->tmA, pl->tmB, pl->tmY, pl->p);
+    return cudaLaunchKernelEx(&cfg, kernel, pl->tmA, pl->tmB, pl->tmY, pl->tmAu, pl->p);
 }
 
 int conv_tc_eligible(const yre_conv_desc& d, char* why, size_t n) {
@@ -1092,6 +1106,15 @@ int conv_tc_eligible(const yre_conv_desc& d, char* why, size_t n) {
     if (d.stride == 2 && !(d.k == 3 && d.x.layout == YRE_PHASE4)) NOPE("stride-2 needs a 3x3 kernel on a PHASE4 input");
     if (d.stride == 1 && d.x.layout != YRE_NHWC) NOPE("stride-1 needs an NHWC input");
     if (d.x.C % 32 || d.x.c_off % 8 || d.x.C_total % 8) NOPE("Cin must be a multiple of 32 (window 16-byte aligned)");
+    if (d.xu.ptr) {
+        if (d.k != 1 || d.stride != 1) NOPE("an upsampled source needs a 1x1 stride-1 conv");
+        if (d.xu.dtype != YRE_BF16 || d.xu.layout != YRE_NHWC) NOPE("upsampled source must be bf16 NHWC");
+        if (d.xu.C % 32 || d.xu.c_off % 8 || d.xu.C_total % 8) NOPE("upsampled source: channels must be a multiple of 32 (window 16-byte aligned)");
+        const int bk = ((d.x.C + d.xu.C) % 64 == 0) ? 64 : 32;
+        if (d.xu.C % bk || d.x.C % bk) NOPE("upsampled source: both sources must be whole K chunks");
+        if ((d.x.H & 1) || (d.x.W & 1)) NOPE("upsampled source: the map must have even extents");
+        if (reinterpret_cast<uintptr_t>(d.xu.ptr) & 127) NOPE("xu must be 128-byte aligned");
+    }
     if (d.y.C % 16) NOPE("Cout must be a multiple of 16");
     const int yal = d.y.dtype == YRE_F32 ? 4 : 8;
     if (d.y.c_off % yal || d.y.C_total % yal) NOPE("output window must be 16-byte aligned");
@@ -1113,12 +1136,14 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     ConvTcPlan* pl = new ConvTcPlan();
     memset(pl, 0, sizeof(*pl));
     TcParams& p = pl->p;
-    const int Cin = d.x.C, Cout = d.y.C, Ho = d.y.H, Wo = d.y.W, B = d.y.B;
+    const int Cu = d.xu.ptr ? d.xu.C : 0;
+    const int Cin = d.x.C + Cu, Cout = d.y.C, Ho = d.y.H, Wo = d.y.W, B = d.y.B;
     p.Ho = Ho; p.Wo = Wo; p.B = B; p.Cin = Cin; p.Cout = Cout; p.x_coff = d.x.c_off;
     p.taps = d.k * d.k;
     p.phase4 = d.stride == 2;
     p.block_k = (Cin % 64 == 0) ? 64 : 32;
     p.kchunks = Cin / p.block_k;
+    p.ku_chunks = Cu / p.block_k; p.xu_coff = d.xu.ptr ? d.xu.c_off : 0; p.xu_rows = d.xu.ptr ? d.xu.H : 0;
     p.layout_type = p.block_k == 64 ? 2u : 4u;
     p.sbo16 = (uint32_t)(8 * p.block_k * 2) >> 4;
 
@@ -1127,6 +1152,8 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     for (int tw = 128; tw >= 1; tw >>= 1)
         for (int th = 128 / tw; th >= 1; th >>= 1) {
             const int tb = 128 / (tw * th);
+            // upsampled source: a patch is a box of whole 2x2 blocks, one box per image, each a whole number of swizzle atoms
+            if (Cu && (tw < 2 || th < 2 || tw * th < 8)) continue;
             const long long tiles = (long long)yre_cdiv(Wo, tw) * yre_cdiv(Ho, th) * yre_cdiv(B, tb);
             if (best < 0 || tiles < best) { best = tiles; btw = tw; bth = th; btb = tb; }
         }
@@ -1290,6 +1317,19 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); }
+    pl->tmAu = pl->tmA;   // unused unless an upsampled source is given
+    if (Cu) {
+        // {C, dup x, W/2, dup y, (H/2) * B}: the duplicated dimensions have stride 0 (accepted by the driver and the TMA
+        // unit, scripts/ubench/tma_dup.cu), the images stack along the row dimension
+        const cuuint64_t Ct = (cuuint64_t)d.xu.C_total, Wu = (cuuint64_t)d.xu.W, Hu = (cuuint64_t)d.xu.H;
+        cuuint64_t gdim[5] = {Ct, 2, Wu, 2, Hu * (cuuint64_t)d.xu.B};
+        cuuint64_t gstr[4] = {0, Ct * 2, 0, Wu * Ct * 2};
+        cuuint32_t box[5] = {(cuuint32_t)p.block_k, 2, (cuuint32_t)(p.tw / 2), 2, (cuuint32_t)(p.th / 2)};
+        cuuint32_t est[5] = {1, 1, 1, 1, 1};
+        r = enc(&pl->tmAu, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d.xu.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(upsampled A) failed with %d", (int)r); }
+    }
     {
         const cuuint64_t K = (cuuint64_t)p.taps * Cin;
         cuuint64_t gdim[2] = {K, (cuuint64_t)Cout};

@@ -79,6 +79,14 @@ int check_conv(const yre_conv_desc* d) {
     if (d->y.layout != YRE_NHWC && d->engine == YRE_ENGINE_TCGEN05) YRE_FAIL(YRE_EUNSUPPORTED, "conv: tcgen05 engine writes NHWC only");
     if (d->res.ptr && (d->res.B != d->y.B || d->res.H != d->y.H || d->res.W != d->y.W || d->res.C != d->y.C))
         YRE_FAIL(YRE_EINVAL, "conv: residual shape mismatch");
+    if (d->xu.ptr) {          // virtual cat([upsample2x(xu), x]) input
+        if (yre_check_view(&d->xu, "conv.xu")) return YRE_EINVAL;
+        if (d->k != 1 || d->stride != 1) YRE_FAIL(YRE_EUNSUPPORTED, "conv: an upsampled source needs a 1x1 stride-1 conv");
+        if (d->xu.layout != YRE_NHWC || d->x.layout != YRE_NHWC || d->xu.dtype != d->x.dtype)
+            YRE_FAIL(YRE_EUNSUPPORTED, "conv: upsampled source must be NHWC and of x's dtype");
+        if (d->xu.B != d->x.B || 2 * d->xu.H != d->x.H || 2 * d->xu.W != d->x.W)
+            YRE_FAIL(YRE_EINVAL, "conv: upsampled source %dx%d is not half of the input %dx%d", d->xu.H, d->xu.W, d->x.H, d->x.W);
+    }
     return YRE_OK;
 }
 
@@ -260,7 +268,7 @@ int yre_plan_rebind(yre_plan* p, const void* old_ptr, void* new_ptr) {
     for (auto& o : p->ops) {
         switch (o.kind) {
             case OP_CONV_TC:
-                if (o.conv.x.ptr == old_ptr || o.conv.w == old_ptr)
+                if (o.conv.x.ptr == old_ptr || o.conv.w == old_ptr || (o.conv.xu.ptr && o.conv.xu.ptr == old_ptr))
                     YRE_FAIL(YRE_EUNSUPPORTED, "plan_rebind: buffer is baked into a TMA tensor map");
                 {
                     const int r = conv_tc_rebind(o.tc, old_ptr, new_ptr);
@@ -271,6 +279,7 @@ int yre_plan_rebind(yre_plan* p, const void* old_ptr, void* new_ptr) {
                 break;
             case OP_CONV_FFMA:
                 fix(o.conv.x.ptr); fix(o.conv.y.ptr); fix(o.conv.res.ptr); fixc(o.conv.w);
+                if (o.conv.xu.ptr) fix(o.conv.xu.ptr);
                 break;
             case OP_STEM:
                 if (o.stem.x_nchw == old_ptr) { o.stem.x_nchw = (const float*)new_ptr; ++n; }

@@ -24,7 +24,7 @@ class View(C.Structure):
 
 class ConvDesc(C.Structure):
     _fields_ = [("x", View), ("y", View), ("res", View), ("w", C.c_void_p), ("bias", C.c_void_p),
-                ("k", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32), ("engine", C.c_int32)]
+                ("k", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32), ("engine", C.c_int32), ("xu", View)]
 
 
 class StemDesc(C.Structure):

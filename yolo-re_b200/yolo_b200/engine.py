@@ -64,6 +64,23 @@ class V:
         return self.t is o.t and self.c_off == o.c_off and self.C == o.C
 
 
+class VCat:
+    """cat([Upsample(2, nearest)(up), rest], channels) that is never materialised (parser.py:159-171, common.py:32-33): the
+    1x1 conv that consumes it reads ``up`` through yre_conv_desc.xu -- on the tcgen05 engine the upsample is a TMA
+    addressing mode (tensor map with two stride-0 dimensions), so the 4x larger upsampled tensor is neither written nor
+    read."""
+    __slots__ = ("up", "rest")
+
+    def __init__(self, up: V, rest: V):
+        assert (2 * up.H, 2 * up.W, up.B) == (rest.H, rest.W, rest.B)
+        self.up, self.rest = up, rest
+
+    B = property(lambda s: s.rest.B)
+    H = property(lambda s: s.rest.H)
+    W = property(lambda s: s.rest.W)
+    C = property(lambda s: s.up.C + s.rest.C)
+
+
 def _null_view() -> L.View:
     return L.View(None, 0, 0, 0, 0, 0, 0, 0, 0)
 
@@ -162,9 +179,13 @@ class Plan:
         raise L.YreError(f"cannot fold {type(m).__name__}")
 
     # -- op emission -------------------------------------------------------------------------------------
-    def conv(self, x: V, w, b, k, stride, silu, out: V | None = None, res: V | None = None, out_dtype=None) -> V:
+    def conv(self, x: V | VCat, w, b, k, stride, silu, out: V | None = None, res: V | None = None, out_dtype=None) -> V:
         cout, cin = w.shape[0], w.shape[1]
         assert cin == x.C, (cin, x.C)
+        xu = None
+        if isinstance(x, VCat):
+            assert k == 1 and stride == 1, "a virtual upsample+concat input needs a 1x1 stride-1 consumer"
+            xu, x = x.up, x.rest
         Ho = (x.H + 2 * (k // 2) - k) // stride + 1
         Wo = (x.W + 2 * (k // 2) - k) // stride + 1
         if out is None:
@@ -173,9 +194,9 @@ class Plan:
         wp = self.dev(w.permute(0, 2, 3, 1), self.tdt)           # [Cout][kh][kw][Cin]
         bp = self.dev(b, torch.float32)
         d = L.ConvDesc(x.c(), out.c(), res.c() if res is not None else _null_view(), wp.data_ptr(), bp.data_ptr(),
-                       k, stride, L.ACT_SILU if silu else L.ACT_NONE, self.engine)
+                       k, stride, L.ACT_SILU if silu else L.ACT_NONE, self.engine, xu.c() if xu is not None else _null_view())
         L.check(self.lib.yre_plan_add_conv(self.h, C.byref(d)), "plan_add_conv")
-        self.trace.append(("conv", dict(x=x, y=out, res=res, w=wp, b=bp, k=k, stride=stride, silu=silu)))
+        self.trace.append(("conv", dict(x=x, y=out, res=res, w=wp, b=bp, k=k, stride=stride, silu=silu, xu=xu)))
         return out
 
     def conv_m(self, m, x: V, out: V | None = None, res: V | None = None, out_dtype=None) -> V:
@@ -414,8 +435,10 @@ class Plan:
         for kind, a in self.trace:
             if kind == "conv":
                 x, y = a["x"], a["y"]
-                out.append(f"conv{a['k']}x{a['k']}s{a['stride']} {x.C}->{y.C} @{y.H}x{y.W} B{y.B}"
-                           f"{' +res' if a['res'] is not None else ''}{' f32out' if y.dtype == L.F32 else ''}")
+                cin = x.C + (a["xu"].C if a.get("xu") is not None else 0)
+                out.append(f"conv{a['k']}x{a['k']}s{a['stride']} {cin}->{y.C} @{y.H}x{y.W} B{y.B}"
+                           f"{' +res' if a['res'] is not None else ''}{' f32out' if y.dtype == L.F32 else ''}"
+                           f"{' up2x' if a.get('xu') is not None else ''}")
             elif kind == "stem":
                 y = a["y"]
                 out.append(f"stem {'u8 ' if a.get('u8') else ''}3->{y.C} @{y.H}x{y.W} B{y.B}")
@@ -482,12 +505,28 @@ def compile_model(model, x: torch.Tensor) -> Plan:
     chan = {"input": Cin}
     for n in names:
         chan[n] = _out_channels(model.layers[n], [chan[s] for s in srcs[n]])
+    # Upsample -> Concat([up, skip]) -> RepNCSPELAN4: the ELAN's first op is a 1x1 conv over the whole concat, which can
+    # read the half-resolution tensor directly (VCat / yre_conv_desc.xu).  Such an Upsample emits no kernel and its half
+    # of the concat buffer is never allocated.
+    lazy_up: dict[str, str] = {}
+    if getattr(model, "fuse_upsample", True):
+        for n in names:
+            if not (isinstance(model.layers[n], B.Concat) and len(srcs[n]) >= 2):
+                continue
+            u = srcs[n][0]
+            if (u != "input" and isinstance(model.layers[u], B.Upsample) and consumers.get(u) == [n] and u not in srcs[n][1:]
+                    and consumers.get(n) and all(isinstance(model.layers[c], B.RepNCSPELAN4) and srcs[c] == [n] for c in consumers[n])
+                    and chan[u] % 64 == 0 and (chan[n] - chan[u]) % 64 == 0):
+                lazy_up[u] = n
+    cat_chan = {n: chan[n] - sum(chan[u] for u, k in lazy_up.items() if k == n) for n in names}
     # where should a layer write?  -> into the slice of the first Concat that consumes it
     dest: dict[str, tuple[str, int]] = {}
     for n in names:
         if isinstance(model.layers[n], B.Concat):
             off = 0
             for s in srcs[n]:
+                if lazy_up.get(s) == n:
+                    continue
                 if s not in dest and s != "input" and not isinstance(model.layers[s], (B.Silence, B.CBLinear, B.Concat)):
                     dest[s] = (n, off)
                 off += chan[s]
@@ -509,7 +548,7 @@ def compile_model(model, x: torch.Tensor) -> Plan:
             return None
         k, off = dest[n]
         if k not in cat_bufs:
-            cat_bufs[k] = p.alloc(H_, W_, chan[k])
+            cat_bufs[k] = p.alloc(H_, W_, cat_chan[k])
         return cat_bufs[k].sl(off, chan[n])
 
     vals: dict[str, object] = {}
@@ -535,6 +574,15 @@ def compile_model(model, x: torch.Tensor) -> Plan:
             vals[n] = p.stem(m, x, ph)
             continue
         a = ins[0] if single else ins
+        if n in lazy_up:                                   # Upsample folded into its consumer's first conv
+            vals[n] = ("lazy_upsample", a)
+            continue
+        if isinstance(m, B.Concat) and n in lazy_up.values():
+            if n not in cat_bufs:
+                cat_bufs[n] = p.alloc(ins[1].H, ins[1].W, cat_chan[n])
+            vals[n] = VCat(ins[0][1], p.concat(ins[1:], cat_bufs[n]))
+            result = vals[n]
+            continue
         if isinstance(m, (B.Conv, B.RepNCSPELAN4, B.ADown, B.SPPELAN, B.Upsample, B.CBFuse)):
             xin = a if isinstance(a, V) else (a[-1] if isinstance(m, B.CBFuse) else a)
             if isinstance(m, B.Conv):
@@ -608,7 +656,8 @@ def model_forward(model, x: torch.Tensor):
         x = x.contiguous()
     else:
         x = x.contiguous().float()
-    key = (tuple(x.shape), x.dtype, x.device.index, model.precision, bool(getattr(model, "main_only", False)))
+    key = (tuple(x.shape), x.dtype, x.device.index, model.precision, bool(getattr(model, "fuse_upsample", True)),
+           bool(getattr(model, "main_only", False)))
     p = model._plans.get(key)
     if p is not None and model.check_weights and p.weight_version != _weights_version(model):
         p = None
