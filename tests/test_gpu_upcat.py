@@ -127,3 +127,30 @@ def test_model_fused_upsample_equals_materialised(cfg, size, prec, request):
     assert launches[0] == launches[1] - 2
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+# ---- paired halo schedule for a single 64-wide N tile (head box tower: 3x3 256->64 on the 80x80 level) ----------------
+@pytest.mark.parametrize("case", [(6, 80, 80, 256, 1, 0), (15, 48, 56, 128, 1, 1), (5, 80, 80, 192, 0, 0)])
+def test_conv_halo_pair_cout64(case):
+    """3x3 stride-1, Cin a multiple of 64, Cout = 64, enough exact 8x16 patches: two patches share every weight box
+    (TcParams::npair == 2 with a 64-column N tile); even / odd patch counts, residual, no activation."""
+    Bn, H, W, Cin, act, res = case
+    lib = L.lib()
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn((Bn, H, W, Cin), generator=g).bfloat16()
+    w = (torch.randn((64, 3, 3, Cin), generator=g) / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn((64,), generator=g)
+    r = torch.randn((Bn, H, W, 64), generator=g).bfloat16()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
+    if act:
+        ref = F.silu(ref)
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    xd, wd, bd, rd = x.to(DEV), w.to(DEV), bias.to(DEV), r.to(DEV)
+    y = torch.full((Bn, H, W, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    d = L.ConvDesc(L.View(xd.data_ptr(), L.BF16, L.NHWC, Bn, H, W, Cin, 0, Cin), L.View(y.data_ptr(), L.BF16, L.NHWC, Bn, H, W, 64, 0, 64),
+                   L.View(rd.data_ptr(), L.BF16, L.NHWC, Bn, H, W, 64, 0, 64) if res else _null(),
+                   wd.data_ptr(), bd.data_ptr(), 3, 1, act, L.ENGINE_TCGEN05)
+    L.check(lib.yre_conv(C.byref(d), torch.cuda.current_stream().cuda_stream), "yre_conv")
+    err = (y.float().cpu().permute(0, 3, 1, 2) - ref).abs().max().item()
+    assert err <= 1.0e-2 * max(1.0, ref.abs().max().item()), f"{case}: max err {err:.4f}"

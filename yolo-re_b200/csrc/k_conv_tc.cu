@@ -1189,6 +1189,9 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         // two patches per weight box when a 128-wide N tile exists and there are enough pairs to fill the machine
         const int want = env_int("YRE_TC_HALO_PAIR", 1);
         if (want && Cout % 128 == 0 && ((mtiles + 1) / 2) * (Cout / 128) >= sms) { p.npair = 2; bn = 128; }
+        // a single 64-wide N tile with a long K (head box tower, 3x3 256->64 @80x80): every patch re-streams the whole weight
+        // matrix (295 KB against 92 KB of halo), so pairing halves what bounds it (L2 -> SM traffic)
+        else if (want >= 1 && env_int("YRE_TC_HALO_PAIR64", 1) && Cout == 64 && p.kchunks >= 2 && (mtiles + 1) / 2 >= sms) { p.npair = 2; bn = 64; }
     }
     p.block_n = bn;
     p.tiles_n = Cout / bn;
