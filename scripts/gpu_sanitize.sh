@@ -1,5 +1,7 @@
 #!/bin/bash
 # compute-sanitizer passes over the kernel unit tests at small shapes: memcheck, racecheck and
+# NOTE (round 2): the GPU pool refuses to run compute-sanitizer (profiles/r02_sanitizer_note.txt); tests/test_gpu_guard.py is the
+# guard-band substitute for the memcheck pass.  The script is kept for pools where the tool is available.
 # synccheck for the tcgen05 / TMA conv family, the bandwidth kernels and NMS.  Run on the GPU box:
 #     bash scripts/gpu_sanitize.sh            # writes gpurun_out/sanitizer_<tool>.txt (+ a one-line verdict per tool)
 # The summaries kept under profiles/r02_sanitizer_*.txt are the tail of these logs.
