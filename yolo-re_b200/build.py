@@ -24,6 +24,9 @@ FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-li
 # (kernel tuning sessions only); the product build reads no environment variables.
 if os.environ.get("YRE_TUNING", "0") not in ("", "0"):
     FLAGS.append("-DYRE_TUNING")
+for _d in os.environ.get("YRE_DEFINES", "").split():       # experiment switches, e.g. YRE_DEFINES="YRE_SILU_F16X2"
+    FLAGS.append("-D" + _d)
+OUT = Path(os.environ.get("YRE_OUT", str(OUT)))              # build an experimental variant next to the product library
 
 
 def _digest() -> str:

@@ -66,7 +66,8 @@ struct TcParams {
     int nacc, acc_stride;           // TMEM accumulator ring (2..6 buffers), columns per buffer
     int ngroups, tgroups, csplit;   // epilogue warpgroups = tgroups (tiles round-robin) x csplit (32-col chunks round-robin)
     int stw, sth, stb;              // the 32 pixels of one TMEM lane quarter as a (stb x sth x stw) sub-patch
-    uint32_t stage_out_bytes;       // bytes of one per-warp staging buffer (32 rows x 32 ch x 2 = 2048)
+    uint32_t stage_out_bytes;       // bytes of one per-warp staging buffer (32 rows x 32 ch x 2 = 2048; 4096 with stage64)
+    int stage64;                    // 1: the epilogue stages and stores 64-column units (128B-swizzled tile, one TMA store per unit)
     // weight-stationary halo variant (conv3_halo_kernel)
     int halo;                       // 1: weight-stationary halo kernel, 2: halo kernel with streamed weights
     int stages_b, tps;              // halo == 2: slots of the weight ring, filter taps per slot (1 or 3)
@@ -370,7 +371,9 @@ __device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base
 // full / empty mbarrier (8 bytes apart per buffer).
 // PF: prefetch the next chunk's tcgen05.ld into a second 32-register buffer (the 168-register / 384-thread kernels); the
 // 512-thread kernels have 128 registers per thread and at most two chunks per tile, so they load each chunk in place.
-template <bool PF, bool CTA2 = false>
+// S64: 64-column staging units (TcParams::stage64) -- a template parameter because with both store paths in one kernel
+// ptxas spilled ~350 bytes in the chunk loop (16 with one path)
+template <bool PF, bool CTA2 = false, bool S64 = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* tmY, const float* sbias, int warp, int lane,
                                               uint32_t tmem_base, uint32_t out_base, uint32_t tfull0, uint32_t tempty0) {
         // ================= epilogue (warp-local, no CTA barrier) =================
@@ -425,9 +428,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             const bool res16 = p.res && !p.res_f32 && valid;
             const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ctot + p.res_coff + n0;
             uint4 rr[4];
-            if (res16 && cs * 32 + 32 <= p.block_n) {
+            const int first_col = S64 ? cs * 64 : cs * 32;         // this warpgroup's first chunk of the tile
+            if (res16 && first_col + 32 <= p.block_n) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + cs * 32 + 8 * i);
+                for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + first_col + 8 * i);
             }
             if (tracer) trace(p.dbg, 2, tn, 20);
             mbar_wait(tfull, acc_phase, p.dbg, 4);
@@ -480,7 +484,49 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
                 if (valid) store_direct<16>(p, f, pix, n0 + col);
             };
             auto full_at = [&](int c) { return c < nchunks && c * 32 + 32 <= block_n; };
-            if (PF) {
+            if (S64) {
+                // 64-column units: the two 32-column chunks of a unit are staged side by side in one 128B-swizzled tile and leave
+                // with ONE TMA store.  The per-store fixed costs (bulk-group wait, proxy fence, two warp syncs, store issue:
+                // ~500 of the ~1100 cycles a chunk takes in the timeline traces, profiles/r02_notes.md) are paid per 64 columns.
+                uint32_t va[32], vb[32];
+                const int nunits = block_n >> 6;
+                const uint32_t sw7 = (uint32_t)(lane & 7);                  // SWIZZLE_128B pattern of this row
+                int u = cs;
+                if (u < nunits) TMEM_LD32(taddr + (uint32_t)(u * 64), va);
+                while (u < nunits) {
+                    const int col = u * 64;
+                    const bool more = u + CS < nunits;
+                    float f[32];
+                    tmem_ld_wait();
+                    TMEM_LD32(taddr + (uint32_t)(col + 32), vb);
+                    epilogue_math<32>(p, sbias, va, f, valid, pix, n0 + col, res16 ? rr : nullptr);
+                    if (res16) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + col + 32 + 8 * i);
+                    }
+                    if (elect_one()) bulk_wait_read<1>();                   // the store that used this buffer two units ago has read it
+                    __syncwarp();
+                    const uint32_t buf = stg + obuf * stage_out;
+                    const uint32_t rowb = buf + (uint32_t)lane * 128u;
+                    store_staged32(f, rowb, 0u, sw7);
+                    tmem_ld_wait();
+                    if (more) TMEM_LD32(taddr + (uint32_t)((u + CS) * 64), va);
+                    epilogue_math<32>(p, sbias, vb, f, valid, pix, n0 + col + 32, res16 ? rr : nullptr);
+                    if (res16 && more) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) rr[i] = *reinterpret_cast<const uint4*>(rrow + (u + CS) * 64 + 8 * i);
+                    }
+                    store_staged32(f, rowb, 4u, sw7);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (elect_one()) {
+                        tma_store_4d(tmY, buf, y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
+                        bulk_commit();
+                    }
+                    obuf ^= 1u;
+                    u += CS;
+                }
+            } else if (PF) {
                 // two register buffers, alternately consumed and refilled: the loop is unrolled by two chunks so that no
                 // buffer is ever copied (a rotating single pair cost 64 register moves per chunk)
                 uint32_t va[32], vb[32];
@@ -529,7 +575,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
 // CTA2: launched as clusters of two CTAs that feed one cta_group::2 MMA (see TcParams::cta2).  Per 256 x N x 16 MMA each
 // SM then reads 4 KB of A + 16 N bytes of B from its shared memory instead of 4 KB + 32 N, and the TMA writes shrink
 // alike -- the shared-memory port was what bounded the one-CTA kernel at N >= 128 (profiles/r01_notes.md).
-template <int KSTEPS, int NT, bool CTA2>
+template <int KSTEPS, int NT, bool CTA2, bool S64>
 __global__ void __launch_bounds__(NT, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAu, const TcParams p) {
@@ -706,7 +752,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
-        epilogue_role<NT == NT_2WG, CTA2>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
+        epilogue_role<NT == NT_2WG, CTA2, S64>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
     }
 
     tc_fence_before();
@@ -876,7 +922,7 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // port with the UMMA operand reads and bounded the generic kernel at N = 128 (8 KB read + 8 KB written per
 // 64-cycle MMA) -- drops by the 4 KB of A per MMA.
 // Warp roles: warp 0 halo producer, warp 2 TMEM alloc + weight producer, warp 1 MMA issuer, warps 4.. epilogue.
-template <int NT>
+template <int NT, bool S64>
 __global__ void __launch_bounds__(NT, 1)
 conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap /*tmAu: generic kernel only*/, const TcParams p) {
@@ -1019,7 +1065,7 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             acc += NPAIR; if (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
-        epilogue_role<NT == NT_2WG>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_t, bar_t + 64u);
+        epilogue_role<NT == NT_2WG, false, S64>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_t, bar_t + 64u);
     }
 
     tc_fence_before();
@@ -1224,7 +1270,6 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
     // bf16 outputs leave through a swizzled staging tile + TMA store; fp32 outputs (raw head logits) store directly
     p.tma_store = (d.y.dtype == YRE_BF16 && bn % 32 == 0 && env_int("YRE_TC_DIRECT_STORE", 0) == 0) ? 1 : 0;
-    p.stage_out_bytes = p.tma_store ? 2048u : 0u;                    // 32 rows x 32 channels x bf16 per buffer
     p.stw = p.tw < 32 ? p.tw : 32;
     p.sth = (32 / p.stw) < p.th ? (32 / p.stw) : p.th;
     p.stb = 32 / (p.stw * p.sth);
@@ -1248,6 +1293,9 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     if (p.npair == 2) { p.nthreads = NT_2WG; p.acc_stride = 128; p.nacc = 4; p.tgroups = 2; p.csplit = 1; }   // group h <-> patch h
     while (p.csplit > 1 && p.csplit > (bn + 31) / 32) --p.csplit;   // every warpgroup owns at least one chunk
     p.ngroups = p.tgroups * p.csplit;
+    // 64-column staging for the 384-thread kernels (they run the register-prefetching epilogue): N tiles that are whole units
+    p.stage64 = (p.tma_store && p.nthreads == NT_2WG && bn % 64 == 0 && env_int("YRE_TC_STAGE64", 1)) ? 1 : 0;
+    p.stage_out_bytes = p.tma_store ? (p.stage64 ? 4096u : 2048u) : 0u;      // 32 rows x 32 (or 64) channels x bf16 per buffer
     const uint32_t n_stage_bufs = 8u * (uint32_t)p.ngroups;         // 4 warps x 2 buffers per group
     const uint32_t align_slack = p.cta2 ? 0u : 1024u;      // the pair kernel relies on (and checks) the declared 1024-byte alignment
     const uint32_t smem_cap = 227u * 1024u - align_slack - 256u - (uint32_t)Cout * 4u;   // alignment slack + barriers + bias copy
@@ -1346,10 +1394,10 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     if (p.tma_store) {
         cuuint64_t gdim[4] = {(cuuint64_t)d.y.C_total, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
         cuuint64_t gstr[3] = {(cuuint64_t)d.y.C_total * 2, (cuuint64_t)Wo * d.y.C_total * 2, (cuuint64_t)Ho * Wo * d.y.C_total * 2};
-        cuuint32_t box[4] = {32u, (cuuint32_t)p.stw, (cuuint32_t)p.sth, (cuuint32_t)p.stb};
+        cuuint32_t box[4] = {p.stage64 ? 64u : 32u, (cuuint32_t)p.stw, (cuuint32_t)p.sth, (cuuint32_t)p.stb};
         cuuint32_t est[4] = {1, 1, 1, 1};
         r = enc(&pl->tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.y.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                p.stage64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(Y) failed with %d", (int)r); }
     } else {
         pl->tmY = pl->tmB;   // unused
@@ -1366,24 +1414,30 @@ template <typename K> static int opt_in_smem(K kernel) {
 int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
     static YrePerDeviceOnce once;
     if (int e = once.run([]() -> int {
-            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, false>)) return r;
-            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, false>)) return r;
-            if (int r = opt_in_smem(conv_tc_kernel<4, NT_3WG, false>)) return r;
-            if (int r = opt_in_smem(conv_tc_kernel<2, NT_3WG, false>)) return r;
-            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, true>)) return r;
-            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, true>)) return r;
-            if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_2WG>)) return r;
-            if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_3WG>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, false, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, false, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, false, true>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, false, true>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_3WG, false, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_3WG, false, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, true, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, true, false>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, true, true>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, true, true>)) return r;
+            if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_2WG, false>)) return r;
+            if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_2WG, true>)) return r;
+            if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_3WG, false>)) return r;
             if (int r = opt_in_smem(conv3_halo_kernel<4, 64>)) return r;
             if (int r = opt_in_smem(conv3_halo_kernel<4, 32>)) return r;
             if (int r = opt_in_smem(conv3_halo_kernel<2, 64>)) return r;
             if (int r = opt_in_smem(conv3_halo_kernel<2, 32>)) return r;
             return YRE_OK;
         })) return e;
-    const bool k64 = pl->p.block_k == 64;
+    const bool k64 = pl->p.block_k == 64, s64 = pl->p.stage64 != 0;
     if (pl->p.halo == 2) {
-        if (pl->p.nthreads == NT_3WG) YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_3WG>, pl->grid, NT_3WG, pl->smem, s, pl));
-        else                          YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_2WG>, pl->grid, NT_2WG, pl->smem, s, pl));
+        if (pl->p.nthreads == NT_3WG) YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_3WG, false>, pl->grid, NT_3WG, pl->smem, s, pl));
+        else if (s64)                 YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_2WG, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+        else                          YRE_CUDA(launch_tc(conv3_halo_stream_kernel<NT_2WG, false>, pl->grid, NT_2WG, pl->smem, s, pl));
         YRE_LAUNCH_CHECK("conv3_halo_stream");
         return YRE_OK;
     }
@@ -1397,17 +1451,21 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
         return YRE_OK;
     }
     if (pl->p.cta2) {                     // N tiles >= 128 only, which always run the two-warpgroup epilogue
-        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, true>, pl->grid, NT_2WG, pl->smem, s, pl));
-        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+        if (k64) { if (s64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, true, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+                   else     YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, true, false>, pl->grid, NT_2WG, pl->smem, s, pl)); }
+        else     { if (s64) YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, true, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+                   else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, true, false>, pl->grid, NT_2WG, pl->smem, s, pl)); }
         YRE_LAUNCH_CHECK("conv_tc (CTA pair)");
         return YRE_OK;
     }
     if (pl->p.nthreads == NT_3WG) {
-        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_3WG, false>, pl->grid, NT_3WG, pl->smem, s, pl));
-        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_3WG, false>, pl->grid, NT_3WG, pl->smem, s, pl));
+        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_3WG, false, false>, pl->grid, NT_3WG, pl->smem, s, pl));
+        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_3WG, false, false>, pl->grid, NT_3WG, pl->smem, s, pl));
     } else {
-        if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, false>, pl->grid, NT_2WG, pl->smem, s, pl));
-        else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, false>, pl->grid, NT_2WG, pl->smem, s, pl));
+        if (k64) { if (s64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, false, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+                   else     YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, false, false>, pl->grid, NT_2WG, pl->smem, s, pl)); }
+        else     { if (s64) YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, false, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+                   else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, false, false>, pl->grid, NT_2WG, pl->smem, s, pl)); }
     }
     YRE_LAUNCH_CHECK("conv_tc");
     return YRE_OK;
