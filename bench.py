@@ -87,29 +87,51 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md).  The nvidia-smi process is
+    started BEFORE the warm-up (its NVML start-up takes driver locks for tens of milliseconds, which would otherwise sit
+    inside the timed region); every line is stamped on arrival and only the lines that arrived between begin() and end()
+    are reported."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index: int, period_ms: int = 100):
+        self.index, self.proc, self.lines, self.period_ms = index, None, [], period_ms
+        self.t0 = self.t1 = None
+
+    def _reader(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln))
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+                                          "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._reader, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        t0 = self.t0 if self.t0 is not None else -math.inf
+        t1 = (self.t1 if self.t1 is not None else math.inf) + 0.02      # a line is printed a few ms after its sample was taken
+        inside = [ln for t, ln in self.lines if t0 <= t <= t1]
+        window = "timed region"
+        if not inside and self.lines:                                   # region shorter than the sampling period: nearest sample
+            mid = 0.5 * (t0 + t1)
+            inside = [min(self.lines, key=lambda tl: abs(tl[0] - mid))[1]]
+            window = "nearest sample to the timed region"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [t.strip() for t in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -120,7 +142,8 @@ class ClockSampler:
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def cpu_reference_step(nodes, nc, sd, x, conf, iou):
@@ -268,6 +291,9 @@ def main():
         return float(t.item())
 
     # ---- warm-up (also compiles the plan) ----
+    sampler = ClockSampler(local, int(os.environ.get("YRE_BENCH_SAMPLER_MS", "100")))
+    if rank == 0:
+        sampler.start()                               # runs through the warm-up; only samples inside the timed region count
     run_public(args.warmup)
     for _ in range(2):
         out, counts, keep = step_resident()
@@ -276,15 +302,14 @@ def main():
     launches_per_step = plan.num_launches + 3
 
     # ---- device-timed throughput, inputs resident, public API ----
-    sampler = ClockSampler(local)
     sync_all()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
     e0.record()
     dets = run_public(args.steps)
     e1.record()
     torch.cuda.synchronize(dev)
+    sampler.end()
     ms_max = allmax(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     value = world * Bn * args.steps / (ms_max / 1e3)

@@ -1247,14 +1247,14 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     p.num_units = p.upn * p.tiles_n;
     // CTA pairs for the wide N tiles of the generic kernel.  What they buy is operand traffic: per 128 x N x 64 k-iteration a
     // CTA pulls 16 KB of A + N * 128 B of B from L2 (and the MMAs read as much from shared memory); a pair halves the B half.
-    // Measured at batch 64 (profiles/r02_notes.md): layers whose main loop dominates (K >= 576, or K = 512 with two N tiles)
-    // gain 7-15 % (1x1 1024->512 @40x40: 110 -> 95 us), short-K tiles are epilogue-bound and LOSE 10-40 % to the cross-CTA
-    // accumulator hand-off, and launches with fewer than four rounds of units lose to the cluster start-up unless K is huge.
+    // Rule from the per-layer sweep at batch 64 (scripts/gpu_sweep.sh, profiles/r02_notes.md): pairs win wherever the main
+    // loop is at least 8 k-iterations long (K >= 512: 1x1 512->256 @80x80 134 -> 108 us, 3x3 128->128 @20x20 19 -> 13 us --
+    // also for launches of a single round of units, which an earlier rule excluded), and for K = 256 when the N tile is 256
+    // wide (1x1 256->256 @160x160: 308 -> 286 us); K = 128 tiles are epilogue-bound and lose 3-10 % to the cross-CTA
+    // accumulator hand-off.
     {
         const long long K_total = (long long)p.taps * Cin;
-        const long long units2 = ((mtiles + 1) / 2) * p.tiles_n;
-        int want = (!p.halo && bn >= 128 && mtiles >= 2 && (K_total >= 576 || (K_total >= 512 && p.tiles_n >= 2)) &&
-                    (units2 >= 2 * sms || K_total >= 4096)) ? 1 : 0;
+        int want = (!p.halo && bn >= 128 && mtiles >= 2 && (K_total >= 512 || (K_total >= 256 && bn >= 256))) ? 1 : 0;
         const int f = env_int("YRE_TC_CTA2", -1);          // tuning builds: 0 = never, 1 = whenever legal
         if (f == 0) want = 0;
         if (f == 1) want = (!p.halo && bn >= 128 && mtiles >= 2) ? 1 : 0;
@@ -1293,8 +1293,12 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     if (p.npair == 2) { p.nthreads = NT_2WG; p.acc_stride = 128; p.nacc = 4; p.tgroups = 2; p.csplit = 1; }   // group h <-> patch h
     while (p.csplit > 1 && p.csplit > (bn + 31) / 32) --p.csplit;   // every warpgroup owns at least one chunk
     p.ngroups = p.tgroups * p.csplit;
-    // 64-column staging for the 384-thread kernels (they run the register-prefetching epilogue): N tiles that are whole units
-    p.stage64 = (p.tma_store && p.nthreads == NT_2WG && bn % 64 == 0 && env_int("YRE_TC_STAGE64", 1)) ? 1 : 0;
+    // 64-column staging for the 384-thread kernels (they run the register-prefetching epilogue): N tiles that are whole units.
+    // 1x1 convs only: they are store/epilogue-bound and gain 25-35 % from the halved store count (1x1 128->128 @160x160:
+    // 208 -> 135 us), while every 3x3 kernel (generic, CTA pair, halo stream) is main-loop bound and LOSES 8-25 % to the
+    // 32 KB of operand ring the larger staging tiles take (3x3 256->256 @80x80: 366 -> 467 us) -- per-layer sweep, r02_notes.md
+    { const int f = env_int("YRE_TC_STAGE64", -1);
+      p.stage64 = (p.tma_store && p.nthreads == NT_2WG && bn % 64 == 0 && (f < 0 ? p.taps == 1 : f != 0)) ? 1 : 0; }
     p.stage_out_bytes = p.tma_store ? (p.stage64 ? 4096u : 2048u) : 0u;      // 32 rows x 32 (or 64) channels x bf16 per buffer
     const uint32_t n_stage_bufs = 8u * (uint32_t)p.ngroups;         // 4 warps x 2 buffers per group
     const uint32_t align_slack = p.cta2 ? 0u : 1024u;      // the pair kernel relies on (and checks) the declared 1024-byte alignment
