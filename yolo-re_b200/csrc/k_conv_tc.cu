@@ -83,6 +83,9 @@ struct TcParams {
     // half-resolution tensor through tmAu -- dims {C, 2, W/2, 2, (H/2) * B} with the two "2" dimensions at global stride 0,
     // so one box {block_k, 2, tw/2, 2, th/2} delivers the tw x th patch of the UPSAMPLED map in the usual row order
     int ku_chunks, xu_coff, xu_rows;      // xu_rows = H/2 (rows of one image in the merged row dimension)
+    // rev: walk the M tiles from the last to the first.  The plan alternates the direction from one conv launch to the next, so a
+    // layer starts with the part of its input that the previous layer wrote LAST -- the part that is still in the 126 MB L2
+    int rev;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -406,18 +409,21 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             if (CTA2) {                           // CTA-pair schedule: cluster c takes units c, c + #clusters, ...
                 const int u = (int)(blockIdx.x >> 1) + j * (int)(gridDim.x >> 1);
                 if (u >= p.num_units) break;
-                const int m = 2 * (u / p.tiles_n) + pair_rank;       // m >= mtiles (odd tile out): loads zero-fill, stores clip
+                int m = 2 * (u / p.tiles_n) + pair_rank;             // m >= mtiles (odd tile out): loads zero-fill, stores clip
+                if (p.rev) m = ((p.mtiles + 1) & ~1) - 1 - m;
                 const int r = m / p.tiles_x;
                 x0 = (m % p.tiles_x) * p.tw; y0 = (r % p.tiles_y) * p.th; b0 = (r / p.tiles_y) * p.tb; n0 = (u % p.tiles_n) * p.block_n;
             } else if (units) {
                 const int P = (int)blockIdx.x + (j / p.npair) * (int)gridDim.x;
                 if (P >= p.num_units) break;
-                const int m = p.npair * (P % p.upn) + (j % p.npair);
+                int m = p.npair * (P % p.upn) + (j % p.npair);
+                if (p.rev) m = p.npair * p.upn - 1 - m;
                 const int r = m / p.tiles_x;
                 x0 = (m % p.tiles_x) * p.tw; y0 = (r % p.tiles_y) * p.th; b0 = r / p.tiles_y; n0 = (P / p.upn) * p.block_n;
             } else {
                 if (t >= p.num_tiles) break;
-                x0 = tc.xt * p.tw; y0 = tc.yt * p.th; b0 = tc.bt * p.tb; n0 = tc.nt * p.block_n;
+                const int xt = p.rev ? p.tiles_x - 1 - tc.xt : tc.xt, yt = p.rev ? p.tiles_y - 1 - tc.yt : tc.yt, bt = p.rev ? p.tiles_b - 1 - tc.bt : tc.bt;
+                x0 = xt * p.tw; y0 = yt * p.th; b0 = bt * p.tb; n0 = tc.nt * p.block_n;
             }
             const int x = x0 + xx, y = y0 + yy, b = b0 + bi;
             const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
@@ -650,11 +656,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int t = w0 + (int)pipe * wstride; t < wtotal; t += (int)NP * wstride, tc.step(p)) {
             int x0, y0, b0, n0;
             if (CTA2) {
-                const int m = 2 * (t / p.tiles_n) + (int)rank, r = m / p.tiles_x;
+                int m = 2 * (t / p.tiles_n) + (int)rank;
+                if (p.rev) m = ((p.mtiles + 1) & ~1) - 1 - m;
+                const int r = m / p.tiles_x;
                 x0 = (m % p.tiles_x) * p.tw; y0 = (r % p.tiles_y) * p.th; b0 = (r / p.tiles_y) * p.tb;
                 n0 = (t % p.tiles_n) * p.block_n + (int)rank * (p.block_n >> 1);     // this CTA's half of the weight tile
             } else {
-                x0 = tc.xt * p.tw; y0 = tc.yt * p.th; b0 = tc.bt * p.tb; n0 = tc.nt * p.block_n;
+                const int xt = p.rev ? p.tiles_x - 1 - tc.xt : tc.xt, yt = p.rev ? p.tiles_y - 1 - tc.yt : tc.yt, bt = p.rev ? p.tiles_b - 1 - tc.bt : tc.bt;
+                x0 = xt * p.tw; y0 = yt * p.th; b0 = bt * p.tb; n0 = tc.nt * p.block_n;
             }
             for (int tap = 0; tap < p.taps; ++tap) {
                 int dx = 0, dy = 0, plane = 0;
@@ -847,7 +856,8 @@ conv3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         TileCur tc;
         tc.init(p, blockIdx.x, (int)gridDim.x);
         for (int t = blockIdx.x; t < p.num_tiles; t += (int)gridDim.x, tc.step(p)) {
-            const int x0 = tc.xt * p.tw, y0 = tc.yt * p.th, b0 = tc.bt;
+            const int x0 = (p.rev ? p.tiles_x - 1 - tc.xt : tc.xt) * p.tw, y0 = (p.rev ? p.tiles_y - 1 - tc.yt : tc.yt) * p.th;
+            const int b0 = p.rev ? p.tiles_b - 1 - tc.bt : tc.bt;
             const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (S + stage);
             mbar_wait(empty, phase ^ 1u, p.dbg, 1);
             if (lane == 0) trace(p.dbg, 0, tn, 1);
@@ -977,7 +987,8 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const int mp = P % p.upn;
             int x0[2], y0[2], b0[2];
             for (uint32_t h = 0; h < NPAIR; ++h) {
-                const int m = (int)NPAIR * mp + (int)h;
+                int m = (int)NPAIR * mp + (int)h;
+                if (p.rev) m = (int)NPAIR * p.upn - 1 - m;
                 const int xt = m % p.tiles_x, r = m / p.tiles_x;
                 x0[h] = xt * p.tw - 1; y0[h] = (r % p.tiles_y) * p.th - 1; b0[h] = r / p.tiles_y;   // b0 >= B for the odd patch out: zero-filled
             }
@@ -1339,6 +1350,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     p.y = d.y.ptr; p.y_f32 = d.y.dtype == YRE_F32; p.y_ctot = d.y.C_total; p.y_coff = d.y.c_off;
     p.res = d.res.ptr; p.res_f32 = d.res.ptr ? d.res.dtype == YRE_F32 : 0;
     p.res_ctot = d.res.ptr ? d.res.C_total : 0; p.res_coff = d.res.ptr ? d.res.c_off : 0;
+    p.rev = 0;
     p.dbg = nullptr;
     if (env_int("YRE_TC_TRACE", 0)) {
         static int* g_dbg = nullptr;
@@ -1476,6 +1488,8 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
 }
 
 void conv_tc_free(ConvTcPlan* p) { delete p; }
+
+void conv_tc_set_reverse(ConvTcPlan* pl, int rev) { pl->p.rev = rev ? 1 : 0; }
 
 int conv_tc_rebind(ConvTcPlan* pl, const void* old_ptr, void* new_ptr) {
     int n = 0;

@@ -1,5 +1,6 @@
 // C ABI glue of libyre.so: error plumbing, standalone op entry points and the flat launch plan.
 #include "yre_common.cuh"
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include <new>
@@ -185,10 +186,25 @@ void yre_plan_destroy(yre_plan* p) { delete p; }
 
 #define PLAN_GUARD(p) if (!(p)) YRE_FAIL(YRE_EINVAL, "null plan")
 
+// Tile-walk direction of the tcgen05 convs of a plan: 1 = alternate from one conv launch to the next (a layer then starts
+// with what its producer wrote last, i.e. with what is still in L2), 0 = always first-to-last.
+static int plan_rev_mode() {
+#ifdef YRE_TUNING
+    const char* v = getenv("YRE_TC_REV");
+    if (v && *v) return atoi(v);
+#endif
+    return 0;
+}
+
 int yre_plan_add_conv(yre_plan* p, const yre_conv_desc* d) {
     PLAN_GUARD(p);
     Op o;
     if (int e = make_conv_op(d, o)) return e;
+    if (o.tc && plan_rev_mode() == 1) {
+        int n_tc = 0;
+        for (const auto& q : p->ops) n_tc += q.kind == OP_CONV_TC;
+        conv_tc_set_reverse(o.tc, n_tc & 1);
+    }
     p->ops.push_back(o);
     return YRE_OK;
 }
