@@ -147,7 +147,7 @@ def test_stem_writes_only_its_output(shape, u8):
         a.check_guards(f"stem {shape} layout {layout} u8={u8}")
 
 
-@pytest.mark.parametrize("shape", [(2, 128, 37, 41), (3, 64, 40, 40), (1, 256, 21, 20)])
+@pytest.mark.parametrize("shape", [(2, 128, 37, 41), (3, 64, 40, 40), (1, 256, 21, 20), (2, 80, 20, 20), (1, 32, 48, 48), (1, 32, 64, 64)])
 def test_pooling_kernels_write_only_their_outputs(shape):
     """K3 (ADown pre-pool, even and odd maps, parity-plane output), K4 (SPP pyramid), K5 (upsample into a concat slice)."""
     Bn, Cn, H, W = shape
@@ -176,8 +176,9 @@ def test_pooling_kernels_write_only_their_outputs(shape):
     L.check(lib.yre_spp_maxpool(C.byref(vs[0]), C.byref(vs[1]), C.byref(vs[2]), C.byref(vs[3]), s), "spp")
     a.check_guards(f"spp {shape}")
     assert torch.equal(cat[..., :Cn], x)
-    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 13, 1, 6).permute(0, 2, 3, 1)
-    assert torch.equal(cat[..., 3 * Cn:].float(), ref)
+    for i, win in enumerate((5, 9, 13)):          # bf16 plane kernel (64 / 32 / 16 / 8 channels per CTA) and the direct fallback
+        ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), win, 1, win // 2).permute(0, 2, 3, 1)
+        assert torch.equal(cat[..., (i + 1) * Cn:(i + 2) * Cn].float(), ref), f"spp window {win} {shape}"
     # upsample into the middle of a wider buffer
     a = Arena()
     a.reserve((Bn, 2 * H, 2 * W, Cn + 64), torch.bfloat16)

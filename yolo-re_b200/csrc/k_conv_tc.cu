@@ -1219,11 +1219,13 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         const long long htiles = (long long)yre_cdiv(Wo, 8) * yre_cdiv(Ho, 16) * B;
         p.halo = d.k == 3 && d.stride == 1 && p.kchunks == 1 && (Cout == 64 || Cout == 32) &&
                  htiles * 3 <= best * 4 && env_int("YRE_TC_HALO", 1) != 0;
-        // larger layers: streamed weights; worth it while the 8x16 patches waste less than the halo saves
+        // larger layers: streamed weights; worth it while the 8x16 patches waste less than the halo saves.  Not for Cout that
+        // tiles into 256-wide N: there the CTA-pair generic kernel (256 x 256 MMAs, half of the weight tile per SM) is
+        // 11 % faster (3x3 256->256 @80x80 B64: 370 -> 327 us, 3x3 512->512 @80x80 B16: 332 -> 296 us)
         // (measured at batch 64: +5..8% on the 80x80 maps that tile exactly, a loss on 40x40 where a sixth of the
         //  patch rows is padding -- so by default only maps without patch waste take this path)
         if (!p.halo && d.k == 3 && d.stride == 1 && p.block_k == 64 && htiles * 100 <= best * env_int("YRE_TC_HALO_SLACK", 100) &&
-            env_int("YRE_TC_HALO", 2) >= 2) p.halo = 2;
+            env_int("YRE_TC_HALO", 2) >= 2 && (Cout % 256 != 0 || env_int("YRE_TC_HALO_WIDE", 0))) p.halo = 2;
         if (p.halo) { btw = 8; bth = 16; btb = 1; best = htiles; }
     }
     p.tw = btw; p.th = bth; p.tb = btb;
@@ -1236,6 +1238,9 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int bn = 0;
     for (int c = 256; c >= 16; c -= 16) if (Cout % c == 0) { bn = c; break; }
+    // 128-wide tiles beat the odd widths between 128 and 256 (3x3 512->640 @40x40: 5 x 128 runs in 118 us, 4 x 160 in 165 us:
+    // four 128-column accumulators and CTA pairs against three unpaired 160-column ones)
+    if (bn > 128 && bn < 256 && Cout % 128 == 0 && env_int("YRE_TC_PREFER128", 1)) bn = 128;
     // keep the machine busy: halve N tiles while there are fewer tiles than SMs
     while (bn >= 64 && bn % 32 == 0 && mtiles * (Cout / bn) < sms) bn /= 2;
     const int force_bn = env_int("YRE_TC_BLOCK_N", 0);
@@ -1365,6 +1370,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
 
     // ---- tensor maps ----
     const CUtensorMapSwizzle swz = p.block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapL2promotion promoA = (CUtensorMapL2promotion)env_int("YRE_TC_L2PROMO_A", (int)CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     CUresult r;
     if (!p.phase4) {
         cuuint64_t gdim[4] = {(cuuint64_t)d.x.C_total, (cuuint64_t)d.x.W, (cuuint64_t)d.x.H, (cuuint64_t)d.x.B};
@@ -1373,7 +1379,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         if (p.halo) { box[1] = 10; box[2] = 18; box[3] = 1; }      // patch + 1-pixel halo
         cuuint32_t est[4] = {1, 1, 1, 1};
         r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.x.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                promoA, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         const cuuint64_t Hp = (cuuint64_t)(d.x.H + 1) / 2, Wp = (cuuint64_t)(d.x.W + 1) / 2, Ct = (cuuint64_t)d.x.C_total;
         cuuint64_t gdim[5] = {Ct, Wp, Hp, (cuuint64_t)d.x.B, 4};
@@ -1381,7 +1387,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         cuuint32_t box[5] = {(cuuint32_t)p.block_k, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tb, 1};
         cuuint32_t est[5] = {1, 1, 1, 1, 1};
         r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d.x.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                promoA, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); }
     pl->tmAu = pl->tmA;   // unused unless an upsampled source is given
@@ -1394,7 +1400,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         cuuint32_t box[5] = {(cuuint32_t)p.block_k, 2, (cuuint32_t)(p.tw / 2), 2, (cuuint32_t)(p.th / 2)};
         cuuint32_t est[5] = {1, 1, 1, 1, 1};
         r = enc(&pl->tmAu, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, d.xu.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
-                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                promoA, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(upsampled A) failed with %d", (int)r); }
     }
     {

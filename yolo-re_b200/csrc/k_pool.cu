@@ -468,6 +468,61 @@ __global__ void __launch_bounds__(256) spp_plane_kernel(DView x, DView y5, DView
     }
 }
 
+// bf16 product path of the plane-resident K4: the plane stays in bf16 (eight channels per 16-byte word), max is taken
+// with packed HMNMX2 -- max() of bf16 values is exact, so the result equals the fp32-staged kernel's bit for bit -- and the
+// column pass stores its result straight to the output slice.  A CTA owns CHK channels of one image; with CHK = 64 a
+// pixel is one full 128-byte line on both the load and the three store sides.
+__device__ __forceinline__ uint4 hmax8(const uint4 a, const uint4 b) {
+    uint4 r;
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r.x) : "r"(a.x), "r"(b.x));
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r.y) : "r"(a.y), "r"(b.y));
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r.z) : "r"(a.z), "r"(b.z));
+    asm("max.bf16x2 %0, %1, %2;" : "=r"(r.w) : "r"(a.w), "r"(b.w));
+    return r;
+}
+
+template <int G>      // G = CHK / 8 sixteen-byte words per pixel
+__global__ void __launch_bounds__(1024) spp_plane_bf16_kernel(DView x, DView y5, DView y9, DView y13) {
+    extern __shared__ __align__(16) uint4 sq[];
+    const int H = x.H, W = x.W, items = H * W * G;
+    uint4* A = sq;
+    uint4* Bf = sq + items;
+    const int b = blockIdx.x, c0 = blockIdx.y * (G * 8);
+    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x.ptr);
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {
+        const int g = i % G, pix = i / G;
+        A[i] = *reinterpret_cast<const uint4*>(xp + dview_pix(x, b, pix / W, pix % W) + c0 + g * 8);
+    }
+    __syncthreads();
+    const DView outs[3] = {y5, y9, y13};
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        for (int i = threadIdx.x; i < items; i += blockDim.x) {          // row pass A -> Bf
+            const int px = (i / G) % W;
+            uint4 m = A[i];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                if (d == 0 || px + d < 0 || px + d >= W) continue;
+                m = hmax8(m, A[i + d * G]);
+            }
+            Bf[i] = m;
+        }
+        __syncthreads();
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(outs[lvl].ptr);
+        for (int i = threadIdx.x; i < items; i += blockDim.x) {          // column pass Bf -> A and the output slice
+            const int g = i % G, pix = i / G, py = pix / W;
+            uint4 m = Bf[i];
+#pragma unroll
+            for (int d = -2; d <= 2; ++d) {
+                if (d == 0 || py + d < 0 || py + d >= H) continue;
+                m = hmax8(m, Bf[i + d * W * G]);
+            }
+            A[i] = m;
+            *reinterpret_cast<uint4*>(op + dview_pix(outs[lvl], b, py, pix % W) + c0 + g * 8) = m;
+        }
+        __syncthreads();
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // K5: nearest x2 (reference: nn.Upsample, parser.py:159-171) written into the consumer's slice
 template <typename T>
@@ -626,6 +681,30 @@ int launch_spp_maxpool(const yre_view& x, const yre_view& y5, const yre_view& y9
         if (y->B != x.B || y->H != x.H || y->W != x.W || y->C != x.C || y->dtype != x.dtype || y->layout != YRE_NHWC)
             YRE_FAIL(YRE_EINVAL, "spp: output views must match the input");
     if (x.layout != YRE_NHWC) YRE_FAIL(YRE_EUNSUPPORTED, "spp: NHWC only");
+    // bf16: plane-resident kernel on 16-byte words, 64 (or 32) channels per CTA when the two bf16 planes fit in shared memory
+    if (x.dtype == YRE_BF16) {
+        int chk = 0;
+        for (int c : {64, 32, 16, 8})        // 20x20 planes: 64 channels per CTA; 40x40 (1280x1280 input): 16
+            if (x.C % c == 0 && (size_t)2 * x.H * x.W * c * 2 <= 112 * 1024) { chk = c; break; }
+        if (chk) {
+            const size_t smem = (size_t)2 * x.H * x.W * chk * 2;
+            static YrePerDeviceOnce once16;
+            if (int e = once16.run([]() -> int {
+                    YRE_CUDA(cudaFuncSetAttribute(spp_plane_bf16_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                    YRE_CUDA(cudaFuncSetAttribute(spp_plane_bf16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                    YRE_CUDA(cudaFuncSetAttribute(spp_plane_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                    YRE_CUDA(cudaFuncSetAttribute(spp_plane_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+                    return YRE_OK;
+                })) return e;
+            dim3 pg((unsigned)x.B, (unsigned)(x.C / chk));
+            if (chk == 64) spp_plane_bf16_kernel<8><<<pg, 1024, smem, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13));
+            else if (chk == 32) spp_plane_bf16_kernel<4><<<pg, 1024, smem, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13));
+            else if (chk == 16) spp_plane_bf16_kernel<2><<<pg, 1024, smem, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13));
+            else                spp_plane_bf16_kernel<1><<<pg, 1024, smem, s>>>(make_dview(x), make_dview(y5), make_dview(y9), make_dview(y13));
+            YRE_LAUNCH_CHECK("spp_plane_bf16");
+            return YRE_OK;
+        }
+    }
     // plane-resident kernel when a (2 x H x W x CHK) fp32 double buffer fits in shared memory
     int chk = 0;
     for (int c : {32, 16, 8})
