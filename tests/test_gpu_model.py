@@ -188,6 +188,24 @@ def test_cuda_graph_replay_equals_eager(gelan_c):
     assert torch.equal(m(xa)[0], y3) and not torch.equal(y3, ya)
 
 
+def test_fresh_outputs_rebind_fp32_tma_store(gelan_c):
+    """Default mode returns NEW tensors every call: the fp32 raw-logit outputs leave through a TMA store, so re-binding
+    them re-encodes the output tensor map (conv_tc_rebind).  Earlier results must stay untouched and equal."""
+    nodes, nc, sd = gelan_c
+    x = G.fractal(2, 320, torch.Generator().manual_seed(5)).to(DEV)
+    m = build("gelan-c", sd, "bf16")
+    y1, r1 = m(x)
+    keep = [r.clone() for r in r1]
+    y2, r2 = m(x)
+    y3, r3 = m(x)
+    torch.cuda.synchronize()
+    assert all(a.data_ptr() != b.data_ptr() for a, b in zip(r1, r2)) and y1.data_ptr() != y2.data_ptr()
+    assert torch.equal(y1, y2) and torch.equal(y2, y3)
+    for a, b, c, k in zip(r1, r2, r3, keep):
+        assert torch.equal(a, k) and torch.equal(b, k) and torch.equal(c, k)
+        assert torch.isfinite(a).all()
+
+
 def test_state_dict_roundtrip_and_replan(gelan_c):
     nodes, nc, sd = gelan_c
     m = build("gelan-c", sd, "fp32")

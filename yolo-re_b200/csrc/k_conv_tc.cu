@@ -368,6 +368,17 @@ __device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base
     }
 }
 
+// 32 fp32 columns of one row (128 bytes) into a SWIZZLE_128B staging tile: 16-byte chunk q lands at chunk (q ^ sw7)
+__device__ __forceinline__ void store_staged32_f32(const float* f, uint32_t row_base, uint32_t sw7) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const uint32_t a = row_base + ((((uint32_t)q) ^ sw7) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a),
+                     "r"(__float_as_uint(f[q * 4 + 0])), "r"(__float_as_uint(f[q * 4 + 1])),
+                     "r"(__float_as_uint(f[q * 4 + 2])), "r"(__float_as_uint(f[q * 4 + 3])) : "memory");
+    }
+}
+
 // Epilogue role of one warp (warps 4..): tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 staging -> TMA store.
 // warpgroup grp = (tg, cs): tile-group tg takes local tiles tg, tg+GT, ...; inside a tile the csplit warpgroups of
 // a tile-group share the 32-column chunks round-robin.  tfull0 / tempty0 = addresses of the first accumulator
@@ -376,7 +387,9 @@ __device__ __forceinline__ void store_staged32(const float* f, uint32_t row_base
 // 512-thread kernels have 128 registers per thread and at most two chunks per tile, so they load each chunk in place.
 // S64: 64-column staging units (TcParams::stage64) -- a template parameter because with both store paths in one kernel
 // ptxas spilled ~350 bytes in the chunk loop (16 with one path)
-template <bool PF, bool CTA2 = false, bool S64 = false>
+// F32T: fp32 outputs (the raw head logits) leave through a 128B-swizzled fp32 staging tile + TMA store as well (generic
+// one-CTA kernel only); a template parameter for the same reason as S64
+template <bool PF, bool CTA2 = false, bool S64 = false, bool F32T = false>
 __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorMap* tmY, const float* sbias, int warp, int lane,
                                               uint32_t tmem_base, uint32_t out_base, uint32_t tfull0, uint32_t tempty0) {
         // ================= epilogue (warp-local, no CTA barrier) =================
@@ -466,7 +479,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
                     if (tracer) trace(p.dbg, 2, tn, 25);
 #endif
                     const uint32_t buf = stg + obuf * stage_out;
-                    store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
+                    if (F32T) store_staged32_f32(f, buf + (uint32_t)lane * 128u, (uint32_t)(lane & 7));
+                    else store_staged32(f, buf + (uint32_t)lane * 64u, 0u, sw);
                     fence_async_smem();
                     __syncwarp();
                     if (elect_one()) {
@@ -581,7 +595,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
 // CTA2: launched as clusters of two CTAs that feed one cta_group::2 MMA (see TcParams::cta2).  Per 256 x N x 16 MMA each
 // SM then reads 4 KB of A + 16 N bytes of B from its shared memory instead of 4 KB + 32 N, and the TMA writes shrink
 // alike -- the shared-memory port was what bounded the one-CTA kernel at N >= 128 (profiles/r01_notes.md).
-template <int KSTEPS, int NT, bool CTA2, bool S64>
+template <int KSTEPS, int NT, bool CTA2, bool S64, bool F32T = false>
 __global__ void __launch_bounds__(NT, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmAu, const TcParams p) {
@@ -761,7 +775,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             while (acc >= NACC) { acc -= NACC; acc_phase ^= 1u; }
         }
     } else if (warp >= 4 && ((warp - 4) >> 2) < p.ngroups) {
-        epilogue_role<NT == NT_2WG, CTA2, S64>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
+        epilogue_role<NT == NT_2WG, CTA2, S64, F32T>(p, &tmY, sbias, warp, lane, tmem_base, out_base, bar_base + 8u * (2u * S), bar_base + 8u * (2u * S + 8u));
     }
 
     tc_fence_before();
@@ -1134,6 +1148,20 @@ struct ConvTcPlan {
     size_t smem;
 };
 
+// output tensor map of the staged TMA store: one box = the 32 pixels of a TMEM lane quarter x 32 (64 with stage64) channels;
+// fp32 outputs use 128-byte rows (32 channels) in a 128B-swizzled tile.  Also used when an output buffer is re-bound.
+static CUresult encode_y(ConvTcPlan* pl, void* ptr) {
+    const auto& p = pl->p;
+    const cuuint64_t es = p.y_f32 ? 4 : 2, ct = (cuuint64_t)p.y_ctot;
+    cuuint64_t gdim[4] = {ct, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B};
+    cuuint64_t gstr[3] = {ct * es, (cuuint64_t)p.Wo * ct * es, (cuuint64_t)p.Ho * p.Wo * ct * es};
+    cuuint32_t box[4] = {p.stage64 ? 64u : 32u, (cuuint32_t)p.stw, (cuuint32_t)p.sth, (cuuint32_t)p.stb};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    return get_encode()(&pl->tmY, p.y_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, gdim, gstr, box, est,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, (p.stage64 || p.y_f32) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 template <typename K>
 static cudaError_t launch_tc(K kernel, int grid, int block, size_t smem, cudaStream_t s, const ConvTcPlan* pl) {
     static const int pdl = env_int("YRE_TC_PDL", 1);
@@ -1286,6 +1314,11 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
     // bf16 outputs leave through a swizzled staging tile + TMA store; fp32 outputs (raw head logits) store directly
     p.tma_store = (d.y.dtype == YRE_BF16 && bn % 32 == 0 && env_int("YRE_TC_DIRECT_STORE", 0) == 0) ? 1 : 0;
+    // fp32 outputs (raw head logits): the full 32-column chunks of a tile go through a fp32 staging tile + TMA store on the
+    // generic one-CTA kernel (a 16-column tail, Cout = 80, still stores directly): one 4 KB bulk store instead of eight
+    // 16-byte stores per lane at a 576-byte pitch
+    const bool f32_tma = d.y.dtype == YRE_F32 && bn >= 32 && !p.halo && !p.cta2 && env_int("YRE_TC_F32_TMA", 1) != 0;
+    if (f32_tma) p.tma_store = 1;
     p.stw = p.tw < 32 ? p.tw : 32;
     p.sth = (32 / p.stw) < p.th ? (32 / p.stw) : p.th;
     p.stb = 32 / (p.stw * p.sth);
@@ -1315,7 +1348,8 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     // 32 KB of operand ring the larger staging tiles take (3x3 256->256 @80x80: 366 -> 467 us) -- per-layer sweep, r02_notes.md
     { const int f = env_int("YRE_TC_STAGE64", -1);
       p.stage64 = (p.tma_store && p.nthreads == NT_2WG && bn % 64 == 0 && (f < 0 ? p.taps == 1 : f != 0)) ? 1 : 0; }
-    p.stage_out_bytes = p.tma_store ? (p.stage64 ? 4096u : 2048u) : 0u;      // 32 rows x 32 (or 64) channels x bf16 per buffer
+    if (f32_tma) p.stage64 = 0;
+    p.stage_out_bytes = p.tma_store ? ((p.stage64 || f32_tma) ? 4096u : 2048u) : 0u;      // 32 rows x 32 (or 64) bf16 / 32 fp32 channels per buffer
     const uint32_t n_stage_bufs = 8u * (uint32_t)p.ngroups;         // 4 warps x 2 buffers per group
     const uint32_t align_slack = p.cta2 ? 0u : 1024u;      // the pair kernel relies on (and checks) the declared 1024-byte alignment
     const uint32_t smem_cap = 227u * 1024u - align_slack - 256u - (uint32_t)Cout * 4u;   // alignment slack + barriers + bias copy
@@ -1414,12 +1448,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     }
     if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r); }
     if (p.tma_store) {
-        cuuint64_t gdim[4] = {(cuuint64_t)d.y.C_total, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B};
-        cuuint64_t gstr[3] = {(cuuint64_t)d.y.C_total * 2, (cuuint64_t)Wo * d.y.C_total * 2, (cuuint64_t)Ho * Wo * d.y.C_total * 2};
-        cuuint32_t box[4] = {p.stage64 ? 64u : 32u, (cuuint32_t)p.stw, (cuuint32_t)p.sth, (cuuint32_t)p.stb};
-        cuuint32_t est[4] = {1, 1, 1, 1};
-        r = enc(&pl->tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.y.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                p.stage64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        r = encode_y(pl, d.y.ptr);
         if (r != CUDA_SUCCESS) { delete pl; YRE_FAIL(YRE_ECUDA, "conv_tc: cuTensorMapEncodeTiled(Y) failed with %d", (int)r); }
     } else {
         pl->tmY = pl->tmB;   // unused
@@ -1446,6 +1475,10 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
             if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, true, false>)) return r;
             if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, true, true>)) return r;
             if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, true, true>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_2WG, false, false, true>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_2WG, false, false, true>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<4, NT_3WG, false, false, true>)) return r;
+            if (int r = opt_in_smem(conv_tc_kernel<2, NT_3WG, false, false, true>)) return r;
             if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_2WG, false>)) return r;
             if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_2WG, true>)) return r;
             if (int r = opt_in_smem(conv3_halo_stream_kernel<NT_3WG, false>)) return r;
@@ -1480,6 +1513,17 @@ int conv_tc_launch(const ConvTcPlan* pl, cudaStream_t s) {
         YRE_LAUNCH_CHECK("conv_tc (CTA pair)");
         return YRE_OK;
     }
+    if (pl->p.y_f32 && pl->p.tma_store) {      // fp32 output through the staged TMA store
+        if (pl->p.nthreads == NT_3WG) {
+            if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_3WG, false, false, true>, pl->grid, NT_3WG, pl->smem, s, pl));
+            else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_3WG, false, false, true>, pl->grid, NT_3WG, pl->smem, s, pl));
+        } else {
+            if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_2WG, false, false, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+            else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_2WG, false, false, true>, pl->grid, NT_2WG, pl->smem, s, pl));
+        }
+        YRE_LAUNCH_CHECK("conv_tc (fp32 out)");
+        return YRE_OK;
+    }
     if (pl->p.nthreads == NT_3WG) {
         if (k64) YRE_CUDA(launch_tc(conv_tc_kernel<4, NT_3WG, false, false>, pl->grid, NT_3WG, pl->smem, s, pl));
         else     YRE_CUDA(launch_tc(conv_tc_kernel<2, NT_3WG, false, false>, pl->grid, NT_3WG, pl->smem, s, pl));
@@ -1500,7 +1544,7 @@ void conv_tc_set_reverse(ConvTcPlan* pl, int rev) { pl->p.rev = rev ? 1 : 0; }
 int conv_tc_rebind(ConvTcPlan* pl, const void* old_ptr, void* new_ptr) {
     int n = 0;
     if (pl->p.y == old_ptr) {
-        if (pl->p.tma_store) return -1;          // output is baked into a TMA tensor map
+        if (pl->p.tma_store && encode_y(pl, new_ptr) != CUDA_SUCCESS) return -1;     // the output is baked into a TMA tensor map
         pl->p.y = new_ptr; ++n;
     }
     if (pl->p.res == old_ptr) { pl->p.res = new_ptr; ++n; }
