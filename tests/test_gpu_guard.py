@@ -82,6 +82,7 @@ CONV_CASES = [
     (2, 50, 19, 32, 32, 3, 0, 0, "tc", 0, 0, 0),         # halo kernel, SWIZZLE_64B
     (7, 48, 56, 128, 128, 3, 0, 0, "tc", 0, 0, 0),       # streamed halo, paired patches (147 patches: odd one out)
     (15, 48, 56, 128, 64, 3, 0, 0, "tc", 64, 64, 0),     # paired halo with a 64-wide N tile
+    (42, 24, 40, 128, 64, 3, 1, 0, "tc", 64, 32, 0),     # paired halo on 8x8 patches of two images (ybx), odd pair count, residual
     (7, 20, 20, 128, 128, 3, 1, 0, "tc", 0, 0, 0),       # CTA pairs, odd number of M tiles
     (2, 16, 16, 256, 160, 1, 0, 1, "tc", 16, 0, 0),      # fp32 output, direct stores, 16-column tail
     (2, 13, 11, 256, 80, 1, 0, 1, "tc", 0, 0, 0),        # raw class logits: Cout = 80

@@ -130,10 +130,13 @@ def test_model_fused_upsample_equals_materialised(cfg, size, prec, request):
 
 
 # ---- paired halo schedule for a single 64-wide N tile (head box tower: 3x3 256->64 on the 80x80 level) ----------------
-@pytest.mark.parametrize("case", [(6, 80, 80, 256, 1, 0), (15, 48, 56, 128, 1, 1), (5, 80, 80, 192, 0, 0)])
+@pytest.mark.parametrize("case", [(6, 80, 80, 256, 1, 0), (15, 48, 56, 128, 1, 1), (5, 80, 80, 192, 0, 0),
+                                  (24, 40, 40, 128, 1, 1), (42, 24, 40, 192, 1, 0), (64, 40, 40, 512, 0, 0)])
 def test_conv_halo_pair_cout64(case):
     """3x3 stride-1, Cin a multiple of 64, Cout = 64, enough exact 8x16 patches: two patches share every weight box
-    (TcParams::npair == 2 with a 64-column N tile); even / odd patch counts, residual, no activation."""
+    (TcParams::npair == 2 with a 64-column N tile); even / odd patch counts, residual, no activation.
+    The 40-wide maps are not tiled by 8x16 patches: they take 8x8 patches of two images (TcParams::ybx, tensor maps with
+    the batch dimension ahead of H) -- even / odd pair counts (300, 315 tiles), residual, the head's 3x3 512->64 @40x40."""
     Bn, H, W, Cin, act, res = case
     lib = L.lib()
     g = torch.Generator().manual_seed(sum(case))

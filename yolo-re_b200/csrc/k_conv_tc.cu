@@ -86,6 +86,11 @@ struct TcParams {
     // rev: walk the M tiles from the last to the first.  The plan alternates the direction from one conv launch to the next, so a
     // layer starts with the part of its input that the previous layer wrote LAST -- the part that is still in the 126 MB L2
     int rev;
+    // ybx (halo == 2 only): a tile is an 8 (x) by 8 (y) patch of TWO images (tb = 2) and its rows run (y, image, x) instead of
+    // (image, y, x): the halo box {C, 10, 2, 10} of a tensor map with the batch dimension ahead of H lands as 20 pixel rows per
+    // image row pair, so the sixteen 8-pixel row groups of the MMA are again one halo row (10 pixels) apart.  Tiles 40x40 maps
+    // exactly (8x16 patches waste a sixth of them); tap (ky, kx) is a shift of ky * 20 + kx pixel rows.
+    int ybx;
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -401,9 +406,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
         const int tg = grp % p.tgroups, cs = grp / p.tgroups, CS = p.csplit;
         const int row = q * 32 + lane;
         const int patch = p.tw * p.th;
-        const int bi = row / patch, rem = row % patch, yy = rem / p.tw, xx = rem % p.tw;
+        const int rem = row % patch;
+        const int bi = p.ybx ? (row / p.tw) % p.tb : row / patch, yy = p.ybx ? row / (p.tw * p.tb) : rem / p.tw, xx = p.ybx ? row % p.tw : rem % p.tw;
         // origin of this warp's 32-pixel sub-patch inside the tile (row 32q)
-        const int r0 = q * 32, sb0 = r0 / patch, sy0 = (r0 % patch) / p.tw, sx0 = (r0 % patch) % p.tw;
+        const int r0 = q * 32;
+        const int sb0 = p.ybx ? (r0 / p.tw) % p.tb : r0 / patch, sy0 = p.ybx ? r0 / (p.tw * p.tb) : (r0 % patch) / p.tw, sx0 = p.ybx ? r0 % p.tw : (r0 % patch) % p.tw;
         const uint32_t stg = out_base + (uint32_t)(warp - 4) * 2u * p.stage_out_bytes;
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);         // SWIZZLE_64B pattern of this row
         const int nchunks = (p.block_n + 31) >> 5;
@@ -432,7 +439,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
                 int m = p.npair * (P % p.upn) + (j % p.npair);
                 if (p.rev) m = p.npair * p.upn - 1 - m;
                 const int r = m / p.tiles_x;
-                x0 = (m % p.tiles_x) * p.tw; y0 = (r % p.tiles_y) * p.th; b0 = r / p.tiles_y; n0 = (P / p.upn) * p.block_n;
+                x0 = (m % p.tiles_x) * p.tw; y0 = (r % p.tiles_y) * p.th; b0 = (r / p.tiles_y) * p.tb; n0 = (P / p.upn) * p.block_n;
             } else {
                 if (t >= p.num_tiles) break;
                 const int xt = p.rev ? p.tiles_x - 1 - tc.xt : tc.xt, yt = p.rev ? p.tiles_y - 1 - tc.yt : tc.yt, bt = p.rev ? p.tiles_b - 1 - tc.bt : tc.bt;
@@ -440,6 +447,8 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
             }
             const int x = x0 + xx, y = y0 + yy, b = b0 + bi;
             const bool valid = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+            // TMA-store coordinates of this warp's 32-pixel box: {c, x, y, image}, or {c, x, image, y} for a ybx tile
+            const int tc1 = x0 + sx0, tc2 = p.ybx ? b0 + sb0 : y0 + sy0, tc3 = p.ybx ? y0 + sy0 : b0 + sb0;
             const long long pix = ((long long)b * p.Ho + y) * p.Wo + x;
             const uint32_t tfull = tfull0 + 8u * acc, tempty = tempty0 + 8u * acc;
             // bf16 residual of the chunk about to be processed: fetched before the accumulator wait / one chunk ahead,
@@ -484,7 +493,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
                     fence_async_smem();
                     __syncwarp();
                     if (elect_one()) {
-                        tma_store_4d(tmY, buf, y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
+                        tma_store_4d(tmY, buf, y_coff + n0 + col, tc1, tc2, tc3);
                         bulk_commit();
                     }
 #ifdef YRE_TUNING
@@ -540,7 +549,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& p, const CUtensorM
                     fence_async_smem();
                     __syncwarp();
                     if (elect_one()) {
-                        tma_store_4d(tmY, buf, y_coff + n0 + col, x0 + sx0, y0 + sy0, b0 + sb0);
+                        tma_store_4d(tmY, buf, y_coff + n0 + col, tc1, tc2, tc3);
                         bulk_commit();
                     }
                     obuf ^= 1u;
@@ -960,7 +969,7 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     constexpr uint32_t ROW_BYTES = 128, KSTEPS = 4;
-    constexpr uint32_t A_BYTES = (180u * ROW_BYTES + 1023u) & ~1023u;
+    const uint32_t A_BYTES = p.a_bytes;                       // 10 x 18 (or 10 x 2 x 10) halo pixels, 1024-aligned slot
     const uint32_t SA = (uint32_t)p.stages, SB = (uint32_t)p.stages_b;
     const uint32_t sA = sbase;
     const uint32_t NPAIR = (uint32_t)p.npair;
@@ -999,21 +1008,23 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         int tn = 0;
         for (int P = blockIdx.x; P < p.num_units; P += (int)gridDim.x) {
             const int mp = P % p.upn;
-            int x0[2], y0[2], b0[2];
-            for (uint32_t h = 0; h < NPAIR; ++h) {
-                int m = (int)NPAIR * mp + (int)h;
-                if (p.rev) m = (int)NPAIR * p.upn - 1 - m;
-                const int xt = m % p.tiles_x, r = m / p.tiles_x;
-                x0[h] = xt * p.tw - 1; y0[h] = (r % p.tiles_y) * p.th - 1; b0[h] = r / p.tiles_y;   // b0 >= B for the odd patch out: zero-filled
-            }
             for (int kc = 0; kc < p.kchunks; ++kc) {
                 const uint32_t full = bar_base + 8u * stage, empty = bar_base + 8u * (SA + stage);
                 mbar_wait(empty, phase ^ 1u, p.dbg, 1);
                 if (lane == 0) trace(p.dbg, 0, tn, 1);
                 if (elect_one()) {
                     mbar_expect_tx(full, NPAIR * p.halo_tx);
-                    for (uint32_t h = 0; h < NPAIR; ++h)
-                        tma_load_4d(sA + (stage * NPAIR + h) * A_BYTES, &tmA, full, p.x_coff + kc * 64, x0[h], y0[h], b0[h]);
+                    for (uint32_t h = 0; h < NPAIR; ++h) {
+                        // patch h of the unit (coordinates re-derived per box: a few integer ops, no per-thread arrays)
+                        int m = (int)NPAIR * mp + (int)h;
+                        if (p.rev) m = (int)NPAIR * p.upn - 1 - m;
+                        const int r = m / p.tiles_x;
+                        const int x0 = (m % p.tiles_x) * p.tw - 1, y0 = (r % p.tiles_y) * p.th - 1;
+                        const int b0 = (r / p.tiles_y) * p.tb;            // b0 >= B for the odd patch out: zero-filled
+                        const uint32_t dst = sA + (stage * NPAIR + h) * A_BYTES;
+                        if (p.ybx) tma_load_4d(dst, &tmA, full, p.x_coff + kc * 64, x0, b0, y0);
+                        else tma_load_4d(dst, &tmA, full, p.x_coff + kc * 64, x0, y0, b0);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) trace(p.dbg, 0, tn, 2);
@@ -1042,12 +1053,14 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        constexpr uint32_t ROW16 = ROW_BYTES >> 4, A16 = A_BYTES >> 4;
+        constexpr uint32_t ROW16 = ROW_BYTES >> 4;
+        const uint32_t A16 = A_BYTES >> 4;
         const uint64_t dA = make_smem_desc(0, 10u * ROW16, p.layout_type);      // 8-row groups one halo row apart
         const uint64_t dB = make_smem_desc(0, p.sbo16, p.layout_type);
         const uint32_t a_hi = (uint32_t)(dA >> 32), b_hi = (uint32_t)(dB >> 32);
         const uint32_t a_lo0 = (uint32_t)dA + (sA >> 4), b_lo0 = (uint32_t)dB + (sB >> 4);
         const uint32_t b16 = p.b_bytes >> 4;
+        const uint32_t yrows = p.ybx ? 20u : 10u;                 // pixel rows between two image rows of the halo tile
         const uint32_t NACC = (uint32_t)p.nacc, TPS = (uint32_t)p.tps, astr = (uint32_t)p.acc_stride;
         uint32_t sa = 0, pha = 0, sb = 0, phb = 0, acc = 0, acc_phase = 0;
         int tn = 0;
@@ -1065,7 +1078,7 @@ conv3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     if (elect_one()) {
                         for (uint32_t i = 0; i < TPS; ++i) {
                             const uint32_t tap = tap0 + i;
-                            const uint32_t shift = ((tap / 3u) * 10u + (tap % 3u)) * ROW16;      // tap shift in pixel rows
+                            const uint32_t shift = ((tap / 3u) * yrows + (tap % 3u)) * ROW16;    // tap shift in pixel rows
                             const uint32_t b_lo = b_lo0 + (sb * TPS + i) * b16;
                             for (uint32_t h = 0; h < NPAIR; ++h) {
                                 const uint32_t a_lo = a_slot + h * A16 + shift;
@@ -1156,6 +1169,12 @@ static CUresult encode_y(ConvTcPlan* pl, void* ptr) {
     cuuint64_t gdim[4] = {ct, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.B};
     cuuint64_t gstr[3] = {ct * es, (cuuint64_t)p.Wo * ct * es, (cuuint64_t)p.Ho * p.Wo * ct * es};
     cuuint32_t box[4] = {p.stage64 ? 64u : 32u, (cuuint32_t)p.stw, (cuuint32_t)p.sth, (cuuint32_t)p.stb};
+    if (p.ybx) {                                                   // {C, W, B, H}, like the input map
+        gdim[2] = (cuuint64_t)p.B; gdim[3] = (cuuint64_t)p.Ho;
+        const cuuint64_t sh = gstr[1], sb = gstr[2];
+        gstr[1] = sb; gstr[2] = sh;
+        box[2] = (cuuint32_t)p.stb; box[3] = (cuuint32_t)p.sth;
+    }
     cuuint32_t est[4] = {1, 1, 1, 1};
     return get_encode()(&pl->tmY, p.y_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, gdim, gstr, box, est,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, (p.stage64 || p.y_f32) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -1255,6 +1274,21 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         if (!p.halo && d.k == 3 && d.stride == 1 && p.block_k == 64 && htiles * 100 <= best * env_int("YRE_TC_HALO_SLACK", 100) &&
             env_int("YRE_TC_HALO", 2) >= 2 && (Cout % 256 != 0 || env_int("YRE_TC_HALO_WIDE", 0))) p.halo = 2;
         if (p.halo) { btw = 8; bth = 16; btb = 1; best = htiles; }
+        // maps that 8x16 patches do not tile but 8x8 ones do (40x40): the same kernel on 8 x 8 patches of TWO images (ybx)
+        const long long htiles2 = (long long)yre_cdiv(Wo, 8) * yre_cdiv(Ho, 8) * yre_cdiv(B, 2);
+        // (only where two patches can share every weight box -- the unpaired halo stream loses to the CTA-pair generic kernel)
+        int sms0 = 148, dev0 = 0;
+        cudaGetDevice(&dev0);
+        cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+        // Measured at batch 64 on 40x40 maps: the single 64-wide N tile with a long K gains (3x3 512->64: 104 -> 81 us, the weight
+        // matrix is re-streamed per patch PAIR instead of per tile), 128-wide tiles lose to the CTA-pair generic kernel
+        // (3x3 128->128: 33.5 -> 40 us: 400 units are 2.7 rounds of long units) -- those need YRE_TC_HALO_YBX=2 (tuning builds)
+        const bool pairable = (Cout % 128 == 0 && ((htiles2 + 1) / 2) * (Cout / 128) >= sms0 && env_int("YRE_TC_HALO_YBX", 1) >= 2) ||
+                              (Cout == 64 && p.kchunks >= 2 && (htiles2 + 1) / 2 >= sms0);
+        if (!p.halo && d.k == 3 && d.stride == 1 && p.block_k == 64 && B % 2 == 0 && htiles2 <= best && Cout % 256 != 0 && pairable &&
+            env_int("YRE_TC_HALO", 2) >= 2 && env_int("YRE_TC_HALO_YBX", 1)) {
+            p.halo = 2; p.ybx = 1; btw = 8; bth = 8; btb = 2; best = htiles2;
+        }
     }
     p.tw = btw; p.th = bth; p.tb = btb;
     p.tiles_x = yre_cdiv(Wo, btw); p.tiles_y = yre_cdiv(Ho, bth); p.tiles_b = yre_cdiv(B, btb);
@@ -1307,7 +1341,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     if (p.cta2) p.num_units = (int)((mtiles + 1) / 2) * p.tiles_n;
     p.a_bytes = (uint32_t)(BLOCK_M * p.block_k * 2);
     if (p.halo) {
-        p.halo_tx = (uint32_t)(10 * 18 * p.block_k * 2);
+        p.halo_tx = (uint32_t)((p.ybx ? 10 * 2 * 10 : 10 * 18) * p.block_k * 2);
         p.a_bytes = (p.halo_tx + 1023u) & ~1023u;
     }
     p.b_bytes = (uint32_t)((p.cta2 ? bn / 2 : bn) * p.block_k * 2);       // a pair's CTA stages half of the weight tile
@@ -1322,6 +1356,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     p.stw = p.tw < 32 ? p.tw : 32;
     p.sth = (32 / p.stw) < p.th ? (32 / p.stw) : p.th;
     p.stb = 32 / (p.stw * p.sth);
+    if (p.ybx) { p.stw = 8; p.stb = 2; p.sth = 2; }          // 32 rows of a (y, image, x) tile = 2 image rows x 2 images x 8 pixels
     // TMEM accumulator ring (nacc buffers of acc_stride columns), epilogue groups and (producer, MMA) pairs.
     // Tile j of a CTA uses accumulator j % nacc, epilogue group j % ngroups and pair j % npipes.  Every
     // mbarrier is waited on by parity, so a buffer must always be served by the SAME group and the SAME pair
@@ -1411,6 +1446,12 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
         cuuint64_t gstr[3] = {(cuuint64_t)d.x.C_total * 2, (cuuint64_t)d.x.W * d.x.C_total * 2, (cuuint64_t)d.x.H * d.x.W * d.x.C_total * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.block_k, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tb};
         if (p.halo) { box[1] = 10; box[2] = 18; box[3] = 1; }      // patch + 1-pixel halo
+        if (p.ybx) {                                               // dimension order {C, W, B, H}: box {64, 10, 2 images, 10}
+            gdim[2] = (cuuint64_t)d.x.B; gdim[3] = (cuuint64_t)d.x.H;
+            const cuuint64_t sh = gstr[1], sb = gstr[2];
+            gstr[1] = sb; gstr[2] = sh;
+            box[2] = 2; box[3] = 10;
+        }
         cuuint32_t est[4] = {1, 1, 1, 1};
         r = enc(&pl->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, d.x.ptr, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                 promoA, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -327,9 +327,11 @@ class Plan:
             ncp = -(-nc // 16) * 16
             raw_full = self.alloc(f.H, f.W, 4 * REG_MAX + ncp, dtype=L.F32)
             raw = raw_full.sl(0, 4 * REG_MAX + nc)
-            if f.H % 16 == 0 and f.W % 8 == 0 and f.H * f.W >= 4096 and c3 % 128 == 0:
-                # large level: the 128-wide N tiles of the cls conv take the paired halo kernel (two patches per
-                # weight box); a merged 64+256 = 320-channel GEMM would fall back to 160-wide unpaired tiles
+            if c3 % 128 == 0 and self.batch * f.H * f.W >= 65536:
+                # large level: separate GEMMs.  The 256-wide cls conv takes CTA pairs with 256-column tiles and the box conv
+                # the paired halo kernel (80x80) or 64-wide tiles; a merged 64+256 = 320-channel GEMM runs as two unpaired
+                # 160-wide tiles (3x3 512->320 @40x40 B64: 337 us merged, 106 + 174 us separate).  Small levels (fewer than
+                # 64 Ki output pixels) stay merged: one launch less is worth more there (20x20 B64: 95 vs 99 us)
                 hb_in, hc_in = self.conv_m(box[i][0], f), self.conv_m(cls[i][0], f)
             else:
                 h1 = self.conv_merged([box[i][0], cls[i][0]], f)
