@@ -31,7 +31,6 @@
 // UTCHMMA/UTMALDG in a serialising ELECT loop.  Measurements behind the design choices: profiles/r01_notes.md.
 #include "yre_common.cuh"
 #include <cuda.h>
-#include <cuda_fp16.h>
 #include <cstring>
 #include <cstdlib>
 
@@ -314,16 +313,8 @@ __device__ __forceinline__ void epilogue_math(const TcParams& p, const float* sb
         for (int i = 0; i < NC / 2; ++i) {
             const float2 h = __fmul2_rn(x2[i], make_float2(0.5f, 0.5f));
             float2 t;
-#ifdef YRE_SILU_F16X2
-            // experiment: one packed MUFU op per two outputs (tanh in f16, |error| <= 2^-11; the rest stays fp32)
-            uint32_t hh, tt;
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hh) : "f"(h.y), "f"(h.x));
-            asm("tanh.approx.f16x2 %0, %1;" : "=r"(tt) : "r"(hh));
-            t = __half22float2(*reinterpret_cast<const __half2*>(&tt));
-#else
             asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(h.x));
             asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(h.y));
-#endif
             x2[i] = __ffma2_rn(h, t, h);
         }
     }
