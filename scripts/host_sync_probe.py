@@ -1,3 +1,4 @@
+"""Probe (GPU box): public-API step loop (counts D2H + list slicing, one batch in flight) against the no-host-sync loop,\nalternating, to separate host cost from clock drift.  Result: profiles/r02_notes.md section 3."""
 import sys, os, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]

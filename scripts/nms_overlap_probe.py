@@ -1,3 +1,4 @@
+"""Probe (GPU box): NMS of batch i on a second stream beside the forward of batch i+1 (two plans = double-buffered outputs)\nagainst the plain single-stream loop.  Result: profiles/r02_notes.md section 3 (1 %, not adopted)."""
 import sys, os, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
