@@ -71,6 +71,8 @@ def run(Bn, H, W, Cin, Cout, k):
 shapes = [(8, 160, 160, 32, 32, 3), (8, 160, 160, 64, 64, 1), (8, 80, 80, 128, 128, 3), (8, 80, 80, 256, 256, 3)]
 if len(sys.argv) > 1 and sys.argv[1] == 'small':
     shapes = [(64, 20, 20, 256, 256, 1), (64, 20, 20, 128, 128, 3), (64, 20, 20, 64, 64, 3)]
+elif len(sys.argv) > 1 and sys.argv[1] == 'halo':
+    shapes = [(64, 80, 80, 64, 64, 3), (64, 160, 160, 32, 32, 3), (64, 160, 160, 64, 64, 3)]
 elif len(sys.argv) > 1 and sys.argv[1] == 'mem':
     shapes = [(64, 80, 80, 128, 128, 1), (64, 40, 40, 256, 256, 1), (64, 40, 40, 1024, 512, 1)]
 for shape in shapes:
