@@ -13,7 +13,10 @@
 //   conv3_halo_kernel         3x3 stride-1, Cin <= 64, Cout 32/64: weights resident in shared memory, one 10x18-pixel
 //                             halo box per 8x16 patch, the nine taps are descriptor shifts of that one tile.
 //   conv3_halo_stream_kernel  3x3 stride-1, Cin a multiple of 64: same halo tile per 64-channel chunk, weight boxes
-//                             streamed through a second ring, optionally two patches per weight box.
+//                             streamed through a second ring, optionally two patches per weight box; on maps that 8x16
+//                             patches do not tile, 8x8 patches of two images (TcParams::ybx).
+// conv_tc_kernel<.., CTA2>: clusters of two CTAs feed one 256-row cta_group::2 MMA (each stages half of the weight tile).
+// Which kernel / tile shape a layer gets is decided in conv_tc_prepare from rules measured per layer (profiles/r02_notes.md).
 // Operands land in 128B- (BLOCK_K=64) or 64B- (BLOCK_K=32) swizzled shared memory that the UMMA smem descriptors read
 // directly.  Accumulators live in a ring of TMEM buffers (6x64, 4x128, 3x160 or 2x256 columns), so the epilogue of
 // one tile overlaps the MMAs of the next ones.  All kernels are persistent (grid = min(work units, SMs)).
@@ -26,7 +29,8 @@
 //   tile and issues its own TMA stores -- no CTA-wide barrier in the steady state.
 // Epilogue: tcgen05.ld -> +bias -> SiLU -> (+residual) -> bf16 -> 64B-swizzled shared-memory staging tile -> TMA store
 // (cp.async.bulk.tensor) into the consumer's channel window (concat-slice write, ragged tile edges clipped by the TMA
-// unit).  fp32 outputs (the raw head logits) use direct 16-byte stores.  All role loops are warp-uniform (elect.sync
+// unit).  fp32 outputs (the raw head logits) take the same route through a fp32 staging tile on the one-CTA generic kernel
+// (direct 16-byte stores elsewhere and for a 16-column tail).  All role loops are warp-uniform (elect.sync
 // picks the issuing lane), which keeps the descriptors in uniform registers -- a lane-0 branch made ptxas wrap every
 // UTCHMMA/UTMALDG in a serialising ELECT loop.  Measurements behind the design choices: profiles/r01_notes.md.
 #include "yre_common.cuh"
