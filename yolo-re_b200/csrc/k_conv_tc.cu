@@ -1302,6 +1302,7 @@ int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sms = env_int("YRE_TC_SMS", sms);          // tuning builds: persistent grids sized for a share of the machine
     int bn = 0;
     for (int c = 256; c >= 16; c -= 16) if (Cout % c == 0) { bn = c; break; }
     // 128-wide tiles beat the odd widths between 128 and 256 (3x3 512->640 @40x40: 5 x 128 runs in 118 us, 4 x 160 in 165 us:
