@@ -15,7 +15,7 @@ def read(v) -> torch.Tensor:
     t = v.t.float()
     if v.layout == NHWC:
         return t[..., v.c_off:v.c_off + v.C].clone()
-    out = torch.zeros(v.B, v.H, v.W, v.C)
+    out = torch.zeros(v.B, v.H, v.W, v.C, device=t.device)
     for py in range(2):
         for px in range(2):
             plane = t[py * 2 + px][..., v.c_off:v.c_off + v.C]
