@@ -510,9 +510,9 @@ def main():
     per_op = [max(t - gap_ms, 0.25 * t) for t in per_op]
     if args.per_op:
         with open(args.per_op, "w") as f:
-            f.write("op,kernel,shape,ms,gflop,tflops,ms_raw\n")
-            for i, ((name, fl), tms, desc) in enumerate(zip(table, per_op, plan.op_descriptions())):
-                f.write(f"{i},{name},{desc},{tms:.5f},{fl / 1e9:.3f},{(fl / (tms / 1e3) / 1e12) if tms > 0 else 0:.1f},{per_op_raw[i]:.5f}\n")
+            f.write("op,kernel,shape,ms,gflop,tflops,ms_raw,variant\n")
+            for i, ((name, fl), tms, desc, var) in enumerate(zip(table, per_op, plan.op_descriptions(), plan.op_variants())):
+                f.write(f"{i},{name},{desc},{tms:.5f},{fl / 1e9:.3f},{(fl / (tms / 1e3) / 1e12) if tms > 0 else 0:.1f},{per_op_raw[i]:.5f},{var}\n")
     peak_burst, peak_sust, peak_gbs, peak_src = peaks()
     fam = {}
     for (name, fl), tms in zip(table, per_op):

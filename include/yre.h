@@ -276,6 +276,11 @@ int  yre_plan_op_flops(const yre_plan* p, double* flops, int32_t cap);
 int  yre_plan_run_op(yre_plan* p, int32_t i, yre_stream_t s);
 /* short static name of op i's kernel family ("conv_tc", "conv_ffma", "stem", ...) */
 const char* yre_plan_op_name(const yre_plan* p, int32_t i);
+/* which kernel variant runs op i and with which tiling, e.g. "generic-cta2 M=1x8x16 N=256 K=16x64 stages=4 s64 tma thr=384
+ * grid=148" (halo-ws = weight-stationary halo kernel, halo-stream[-ybx] = streamed-weight halo kernel, generic[-cta2] =
+ * tap-by-tap implicit GEMM [on CTA pairs]); non-conv ops report their family name.  Makes the per-layer kernel selection
+ * visible (there is no silent fallback: a conv that tcgen05 declines shows up as "conv_ffma"). */
+int  yre_plan_op_variant(const yre_plan* p, int32_t i, char* out, int32_t cap);
 
 #ifdef __cplusplus
 }

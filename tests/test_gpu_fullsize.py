@@ -162,3 +162,37 @@ def test_full_size_batch_permutation_and_nms(request):
     for b_ in range(Bn):
         assert cnt[b_] == len(ref[b_])
         assert np.array_equal(out[b_, :cnt[b_]].cpu().numpy(), ref[b_])
+
+
+def test_kernel_selection_rules_at_config_2(request):
+    """The per-layer kernel selection (conv_tc_prepare, rules measured in profiles/r02_notes.md) is visible through
+    yre_plan_op_variant; pin what the full-size config-2 plan gets so that a rule change shows up here."""
+    name, img, Bn = CONFIGS[2]
+    model = _model(name, request)
+    x = make_inputs(Bn, img, seed=7).to(DEV)
+    with torch.cuda.device(x.device):
+        p = E.compile_model(model, x)
+    rows = [(d, v) for (n, _), d, v in zip(p.op_table(), p.op_descriptions(), p.op_variants()) if n == "conv_tc"]
+    assert len(rows) == p.num_tcgen05 and "conv_ffma" not in [n for n, _ in p.op_table()]
+
+    def variants(prefix):
+        got = {v.split(" thr=")[0] for d, v in rows if d.startswith(prefix)}
+        assert got, prefix
+        return got
+
+    for d, v in rows:
+        if d.startswith("conv3x3"):
+            assert " s64" not in v, (d, v)                                   # 64-column staging is for 1x1 convs only
+        if "f32out" in d:
+            assert " tma-f32" in v, (d, v)                                   # raw logits leave through the fp32 TMA store
+        else:
+            assert " tma" in v and " direct" not in v, (d, v)
+    assert all(v.startswith("generic-cta2") and " N=256 " in v for v in variants("conv3x3s1 256->256 @80x80"))
+    assert all(v.startswith("halo-stream ") and " pair" in v and " N=128 " in v for v in variants("conv3x3s1 128->128 @80x80"))
+    assert all(v.startswith("halo-stream ") and " pair" in v and " N=64 " in v for v in variants("conv3x3s1 256->64 @80x80"))
+    assert all(v.startswith("halo-stream-ybx") and " pair" in v for v in variants("conv3x3s1 512->64 @40x40"))
+    assert all(v.startswith("halo-ws") for v in variants("conv3x3s1 32->32 @160x160") | variants("conv3x3s1 64->64 @80x80"))
+    assert all(v.startswith("generic ") and " s64" in v for v in variants("conv1x1s1 128->128 @80x80"))     # K = 128: no CTA pairs
+    assert all(v.startswith("generic-cta2") and " s64" in v for v in variants("conv1x1s1 256->256 @160x160"))
+    assert all(v.startswith("generic-cta2") for v in variants("conv3x3s1 128->128 @20x20") | variants("conv3x3s1 128->128 @40x40")
+               | variants("conv1x1s1 1024->512 @40x40") | variants("conv3x3s2 64->128 @160x160"))

@@ -1587,6 +1587,15 @@ void conv_tc_free(ConvTcPlan* p) { delete p; }
 
 void conv_tc_set_reverse(ConvTcPlan* pl, int rev) { pl->p.rev = rev ? 1 : 0; }
 
+// Human-readable kernel variant and tile shape of a prepared conv (yre_plan_op_variant): which of the tcgen05 kernels runs
+// the layer and with which tiling, so that the selection rules above are visible per layer (plan.op_table(), bench --per-op).
+void conv_tc_describe(const ConvTcPlan* pl, char* out, size_t n) {
+    const auto& p = pl->p;
+    const char* k = p.halo == 1 ? "halo-ws" : p.halo == 2 ? (p.ybx ? "halo-stream-ybx" : "halo-stream") : (p.cta2 ? "generic-cta2" : "generic");
+    snprintf(out, n, "%s M=%dx%dx%d N=%d K=%dx%d stages=%d%s%s%s thr=%d grid=%d", k, p.tb, p.th, p.tw, p.block_n, p.taps * p.kchunks, p.block_k,
+             p.stages, p.npair == 2 ? " pair" : "", p.stage64 ? " s64" : "", p.tma_store ? (p.y_f32 ? " tma-f32" : " tma") : " direct", p.nthreads, pl->grid);
+}
+
 int conv_tc_rebind(ConvTcPlan* pl, const void* old_ptr, void* new_ptr) {
     int n = 0;
     if (pl->p.y == old_ptr) {

@@ -353,5 +353,12 @@ const char* yre_plan_op_name(const yre_plan* p, int32_t i) {
     if (!p || i < 0 || (size_t)i >= p->ops.size()) return "";
     return op_name(p->ops[i].kind);
 }
+int yre_plan_op_variant(const yre_plan* p, int32_t i, char* out, int32_t cap) {
+    if (!p || !out || cap <= 0 || i < 0 || (size_t)i >= p->ops.size()) return YRE_EINVAL;
+    const Op& o = p->ops[i];
+    if (o.kind == OP_CONV_TC && o.tc) conv_tc_describe(o.tc, out, (size_t)cap);
+    else snprintf(out, (size_t)cap, "%s", op_name(o.kind));
+    return YRE_OK;
+}
 
 }  // extern "C"

@@ -147,7 +147,9 @@ int conv_tc_eligible(const yre_conv_desc& d, char* why, size_t why_len);
 int conv_tc_prepare(const yre_conv_desc& d, ConvTcPlan** out);
 int conv_tc_launch(const ConvTcPlan* p, cudaStream_t s);
 void conv_tc_free(ConvTcPlan* p);
-void conv_tc_set_reverse(ConvTcPlan* p, int rev);                        // walk the M tiles last-to-first
+void conv_tc_set_reverse(ConvTcPlan* p, int rev);
+void conv_tc_describe(const ConvTcPlan* p, char* out, size_t n);          // kernel variant + tile shape, for yre_plan_op_variant
+                        // walk the M tiles last-to-first
 int conv_tc_rebind(ConvTcPlan* p, const void* old_ptr, void* new_ptr);   // patches y/res only
 int launch_stem(const yre_stem_desc& d, cudaStream_t s);
 int launch_adown_prepool(const yre_view& x, const yre_view& avg_lo, const yre_view& max_hi, cudaStream_t s);

@@ -102,6 +102,7 @@ SYMBOLS = {
     "yre_plan_num_tcgen05": (C.c_int, [C.c_void_p]),
     "yre_plan_op_flops": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int32]),
     "yre_plan_op_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
+    "yre_plan_op_variant": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]),
 }
 
 _lib = None

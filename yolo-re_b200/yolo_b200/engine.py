@@ -431,6 +431,14 @@ class Plan:
         self.lib.yre_plan_op_flops(self.h, fl, n)
         return [(self.lib.yre_plan_op_name(self.h, i).decode(), fl[i]) for i in range(n)]
 
+    def op_variants(self) -> list[str]:
+        """Kernel variant + tiling of every recorded op (yre_plan_op_variant), same order as op_table()."""
+        out, buf = [], C.create_string_buffer(160)
+        for i in range(self.lib.yre_plan_num_ops(self.h)):
+            L.check(self.lib.yre_plan_op_variant(self.h, i, buf, 160), "plan_op_variant")
+            out.append(buf.value.decode())
+        return out
+
     def op_descriptions(self) -> list[str]:
         """Human-readable shape of every recorded op (same order as op_table())."""
         out = []
